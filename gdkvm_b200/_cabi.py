@@ -1,0 +1,71 @@
+"""ctypes view of include/gdkvm_gdr.h.  The library is loaded lazily and loudly: there is no
+fallback implementation behind it."""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+from ._build import LIB_PATH
+
+GDKVM_ABI_VERSION = 1
+GDKVM_F32, GDKVM_BF16 = 0, 1
+FLAG_FORCE_RECURRENT, FLAG_FORCE_CHUNKED, FLAG_FLAT_CHUNKS = 0x1, 0x2, 0x4
+
+EXPORTED_SYMBOLS = (
+    "gdkvm_abi_version", "gdkvm_strerror", "gdkvm_last_cuda_error",
+    "gdkvm_gdr_fwd", "gdkvm_gdr_plan", "gdkvm_launch_count",
+)
+
+
+class GdkvmGdrParams(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32),
+        ("flags", ctypes.c_uint32),
+        ("q", ctypes.c_void_p), ("k", ctypes.c_void_p), ("v", ctypes.c_void_p),
+        ("g", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+        ("initial_state", ctypes.c_void_p), ("o", ctypes.c_void_p), ("final_state", ctypes.c_void_p),
+        ("q_stride", ctypes.c_int64 * 3), ("k_stride", ctypes.c_int64 * 3), ("v_stride", ctypes.c_int64 * 3),
+        ("o_stride", ctypes.c_int64 * 3), ("g_stride", ctypes.c_int64 * 3), ("beta_stride", ctypes.c_int64 * 3),
+        ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("H", ctypes.c_int32),
+        ("K", ctypes.c_int32), ("V", ctypes.c_int32),
+        ("frame_tokens", ctypes.c_int32), ("io_dtype", ctypes.c_int32), ("gate_dtype", ctypes.c_int32),
+        ("scale", ctypes.c_float), ("reserved", ctypes.c_int32),
+    ]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> ctypes.CDLL:
+    """dlopen gdkvm_b200/libgdkvm_gdr.so; raises if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError(
+                    f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                    "gdkvm_b200 has no CPU or PyTorch fallback for the GDR/LKVA op.")
+            lib = ctypes.CDLL(LIB_PATH)
+            lib.gdkvm_abi_version.restype = ctypes.c_int
+            lib.gdkvm_strerror.restype = ctypes.c_char_p
+            lib.gdkvm_strerror.argtypes = [ctypes.c_int]
+            lib.gdkvm_last_cuda_error.restype = ctypes.c_int
+            lib.gdkvm_gdr_fwd.restype = ctypes.c_int
+            lib.gdkvm_gdr_fwd.argtypes = [ctypes.POINTER(GdkvmGdrParams), ctypes.c_void_p]
+            lib.gdkvm_gdr_plan.restype = ctypes.c_int
+            lib.gdkvm_gdr_plan.argtypes = [ctypes.POINTER(GdkvmGdrParams)]
+            lib.gdkvm_launch_count.restype = ctypes.c_uint64
+            if lib.gdkvm_abi_version() != GDKVM_ABI_VERSION:
+                raise RuntimeError("libgdkvm_gdr.so ABI version mismatch; rebuild")
+            _lib = lib
+    return _lib
+
+
+def strerror(rc: int) -> str:
+    return load().gdkvm_strerror(rc).decode()
+
+
+def launch_count() -> int:
+    return int(load().gdkvm_launch_count())

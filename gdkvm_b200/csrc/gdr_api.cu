@@ -1,0 +1,118 @@
+// C-ABI of the GDKVM memory op (see include/gdkvm_gdr.h).  Validation + dispatch only; no torch
+// types, no allocation of user-visible memory, no host synchronisation.
+#include <atomic>
+#include <mutex>
+
+#include "gdr_common.cuh"
+
+namespace gdkvm {
+
+static std::atomic<uint64_t> g_launches{0};
+static thread_local int tl_last_cuda_error = 0;
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+namespace {
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Shape / dtype / alignment checks shared by plan() and fwd().  No GPU needed.
+int validate(const GdkvmGdrParams* p) {
+    if (p == nullptr) return GDKVM_ERR_NULL;
+    if (p->struct_size != sizeof(GdkvmGdrParams)) return GDKVM_ERR_ABI;
+    if (p->io_dtype != GDKVM_F32 && p->io_dtype != GDKVM_BF16) return GDKVM_ERR_DTYPE;
+    if (p->gate_dtype != GDKVM_F32 && p->gate_dtype != GDKVM_BF16) return GDKVM_ERR_DTYPE;
+    if (p->B <= 0 || p->H <= 0 || p->T < 0 || p->V <= 0) return GDKVM_ERR_SHAPE;
+    if (p->K != 32 && p->K != 64 && p->K != 128) return GDKVM_ERR_SHAPE;
+    if ((int64_t)p->B * p->H > 0x7fffffff) return GDKVM_ERR_SHAPE;
+    if (p->frame_tokens < 0) return GDKVM_ERR_SHAPE;
+    if (p->frame_tokens > 0 && p->T % p->frame_tokens != 0) return GDKVM_ERR_SHAPE;
+    if (p->T > 0 && (!p->q || !p->k || !p->v || !p->g || !p->beta || !p->o)) return GDKVM_ERR_NULL;
+    if ((p->flags & GDKVM_FLAG_FORCE_RECURRENT) && (p->flags & GDKVM_FLAG_FORCE_CHUNKED)) return GDKVM_ERR_UNSUPPORTED;
+    // q/k rows are fetched with 16-byte vector loads (both kernels); TMA needs the same of v/o.
+    const int64_t es = p->io_dtype == GDKVM_BF16 ? 2 : 4;
+    if (p->T > 0) {
+        if (!aligned16(p->q) || !aligned16(p->k)) return GDKVM_ERR_ALIGN;
+        for (int i = 0; i < 3; ++i)
+            if ((p->q_stride[i] * es) % 16 != 0 || (p->k_stride[i] * es) % 16 != 0) return GDKVM_ERR_ALIGN;
+    }
+    if ((p->initial_state && (reinterpret_cast<uintptr_t>(p->initial_state) & 3u)) ||
+        (p->final_state && (reinterpret_cast<uintptr_t>(p->final_state) & 3u)))
+        return GDKVM_ERR_ALIGN;
+    return GDKVM_OK;
+}
+
+int pick(const GdkvmGdrParams* p) {
+    if (p->flags & GDKVM_FLAG_FORCE_RECURRENT) return 0;
+    const bool ok = chunked_supports(*p);
+    if (p->flags & GDKVM_FLAG_FORCE_CHUNKED) return ok ? 1 : GDKVM_ERR_UNSUPPORTED;
+    return ok ? 1 : 0;
+}
+
+// compute capability of the current device, cached per device ordinal
+int device_is_sm100(bool* ok) {
+    static std::mutex mu;
+    static int cached[64];  // 0 unknown, 1 yes, 2 no
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev < 0 || dev >= 64) { *ok = false; return 0; }
+    std::lock_guard<std::mutex> lk(mu);
+    if (cached[dev] == 0) {
+        int major = 0;
+        e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        if (e != cudaSuccess) return (int)e;
+        cached[dev] = major == 10 ? 1 : 2;
+    }
+    *ok = cached[dev] == 1;
+    return 0;
+}
+
+}  // namespace
+}  // namespace gdkvm
+
+extern "C" {
+
+int gdkvm_abi_version(void) { return GDKVM_ABI_VERSION; }
+
+const char* gdkvm_strerror(int status) {
+    switch (status) {
+        case GDKVM_OK: return "ok";
+        case GDKVM_ERR_NULL: return "a required pointer is NULL";
+        case GDKVM_ERR_ABI: return "GdkvmGdrParams.struct_size does not match this library (ABI mismatch)";
+        case GDKVM_ERR_SHAPE: return "unsupported shape (need B,H,V>=1, T>=0, K in {32,64,128}, T % frame_tokens == 0)";
+        case GDKVM_ERR_DTYPE: return "unknown dtype enum";
+        case GDKVM_ERR_ALIGN: return "q/k pointers and strides must be 16-byte aligned; states 4-byte aligned";
+        case GDKVM_ERR_ARCH: return "device is not sm_100 (B200); this library has no fallback path";
+        case GDKVM_ERR_CUDA: return "CUDA call failed (see gdkvm_last_cuda_error)";
+        case GDKVM_ERR_UNSUPPORTED: return "the forced kernel path does not support this problem";
+        default: return "unknown gdkvm status";
+    }
+}
+
+int gdkvm_last_cuda_error(void) { return gdkvm::tl_last_cuda_error; }
+
+uint64_t gdkvm_launch_count(void) { return gdkvm::g_launches.load(std::memory_order_relaxed); }
+
+int gdkvm_gdr_plan(const GdkvmGdrParams* params) {
+    const int rc = gdkvm::validate(params);
+    if (rc != GDKVM_OK) return rc;
+    return gdkvm::pick(params);
+}
+
+int gdkvm_gdr_fwd(const GdkvmGdrParams* params, void* cuda_stream) {
+    int rc = gdkvm::validate(params);
+    if (rc != GDKVM_OK) return rc;
+    const int path = gdkvm::pick(params);
+    if (path < 0) return path;
+    bool sm100 = false;
+    int ce = gdkvm::device_is_sm100(&sm100);
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    if (!sm100) return GDKVM_ERR_ARCH;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ce = path == 1 ? gdkvm::launch_chunked(*params, stream) : gdkvm::launch_recurrent(*params, stream);
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    return GDKVM_OK;
+}
+
+}  // extern "C"

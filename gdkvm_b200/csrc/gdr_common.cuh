@@ -1,0 +1,31 @@
+// Shared declarations of the GDKVM memory-op kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gdkvm_gdr.h"
+
+namespace gdkvm {
+
+// Launchers (defined in gdr_recurrent.cu / gdr_chunked_sm100.cu). Return a cudaError_t as int.
+int launch_recurrent(const GdkvmGdrParams& p, cudaStream_t stream);
+int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream);
+// Host-side eligibility test of the chunked tcgen05 kernel (no GPU needed).
+bool chunked_supports(const GdkvmGdrParams& p);
+
+void count_launch();
+
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ void from_f32(float& d, float x) { d = x; }
+__device__ __forceinline__ void from_f32(__nv_bfloat16& d, float x) { d = __float2bfloat16_rn(x); }
+
+// gate / beta scalar loads with a runtime dtype (they are 2 of ~650 values per token-head)
+__device__ __forceinline__ float load_gate(const void* base, int64_t idx, int dtype) {
+    return dtype == GDKVM_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx])
+                               : reinterpret_cast<const float*>(base)[idx];
+}
+
+}  // namespace gdkvm

@@ -1,0 +1,174 @@
+"""torch.library boundary of the GDKVM memory op.
+
+``torch.ops.gdkvm.gdr_lkva`` keeps the call surface BASELINE.json ``north_star`` fixes for the
+reference memory module -- ``(q, k, v, gate, beta, initial_state) -> (readout, final_state)`` --
+which is argument-compatible with ``fla.ops.gated_delta_rule.chunk_gated_delta_rule``
+(fla/ops/gated_delta_rule/chunk.py:365-377), so the upstream encoder -> KPFF -> memory -> decoder
+pipeline can swap one import.  The reference tree itself has no code for this path
+(reference README.md:1,36-38); the concept is named at README.md:20 and
+website/src/content/homepage/en.json:20.
+
+Only a CUDA implementation is registered.  There is deliberately no CPU kernel, no Triton and no
+flash-linear-attention dispatch: CPU tensors raise from the dispatcher, and a missing
+``libgdkvm_gdr.so`` raises from the loader.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+
+__all__ = ["gdr_lkva", "gdr_lkva_out", "chunk_gated_delta_rule", "plan", "launch_count"]
+
+_DT = {torch.float32: _cabi.GDKVM_F32, torch.bfloat16: _cabi.GDKVM_BF16}
+
+
+def _strides3(t: torch.Tensor):
+    s = t.stride()
+    return (ctypes.c_int64 * 3)(s[0], s[1], s[2])
+
+
+def _make_params(q, k, v, g, beta, o, s0, sT, scale, frame_tokens, flags) -> _cabi.GdkvmGdrParams:
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    p = _cabi.GdkvmGdrParams()
+    p.struct_size = ctypes.sizeof(_cabi.GdkvmGdrParams)
+    p.flags = int(flags)
+    p.q, p.k, p.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    p.g, p.beta = g.data_ptr(), beta.data_ptr()
+    p.initial_state = s0.data_ptr() if s0 is not None else None
+    p.o = o.data_ptr()
+    p.final_state = sT.data_ptr() if sT is not None else None
+    p.q_stride, p.k_stride, p.v_stride = _strides3(q), _strides3(k), _strides3(v)
+    p.o_stride, p.g_stride, p.beta_stride = _strides3(o), _strides3(g), _strides3(beta)
+    p.B, p.T, p.H, p.K, p.V = B, T, H, K, V
+    p.frame_tokens = int(frame_tokens)
+    p.io_dtype = _DT[q.dtype]
+    p.gate_dtype = _DT[g.dtype]
+    p.scale = float(scale)
+    return p
+
+
+def _check(q, k, v, g, beta, initial_state):
+    if q.dim() != 4 or k.shape != q.shape or v.dim() != 4 or v.shape[:3] != q.shape[:3]:
+        raise ValueError("expected q,k [B,T,H,K] and v [B,T,H,V]")
+    if g.shape != q.shape[:3] or beta.shape != q.shape[:3]:
+        raise ValueError("expected g,beta [B,T,H]")
+    if q.dtype not in _DT or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise TypeError("q,k,v must share one dtype of {float32, bfloat16}")
+    if g.dtype not in _DT or beta.dtype != g.dtype:
+        raise TypeError("g,beta must share one dtype of {float32, bfloat16}")
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        if t.stride(-1) != 1:
+            raise ValueError(f"{name}: innermost dimension must be contiguous")
+    if initial_state is not None:
+        B, T, H, K = q.shape
+        if initial_state.shape != (B, H, K, v.shape[-1]) or initial_state.dtype != torch.float32:
+            raise ValueError("initial_state must be fp32 [B,H,K,V]")
+
+
+torch.library.define(
+    "gdkvm::gdr_lkva",
+    "(Tensor q, Tensor k, Tensor v, Tensor g, Tensor beta, float? scale=None, "
+    "Tensor? initial_state=None, bool output_final_state=True, int frame_tokens=0, int flags=0) "
+    "-> (Tensor, Tensor)",
+)
+
+
+def gdr_lkva_out(q, k, v, g, beta, o, final_state=None, scale=None, initial_state=None,
+                 frame_tokens=0, flags=0) -> None:
+    """Launch the op into caller-owned ``o`` (and ``final_state``) on the current stream.
+
+    This is the C-ABI call with torch tensors as the buffer owners: no allocation, no sync.
+    Used by the torch.library op below and by the host-buffer pipeline (gdkvm_b200.host).
+    """
+    _check(q, k, v, g, beta, initial_state)
+    if not q.is_cuda:
+        raise RuntimeError("gdkvm_b200 runs on a B200 only; there is no CPU implementation of gdr_lkva")
+    lib = _cabi.load()
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    if o.shape != (B, T, H, V) or o.dtype != q.dtype or o.stride(-1) != 1:
+        raise ValueError("o must be [B,T,H,V] in q.dtype with a contiguous last dimension")
+    if final_state is not None and (final_state.shape != (B, H, K, V) or final_state.dtype != torch.float32
+                                    or not final_state.is_contiguous()):
+        raise ValueError("final_state must be contiguous fp32 [B,H,K,V]")
+    if initial_state is not None and not initial_state.is_contiguous():
+        raise ValueError("initial_state must be contiguous")
+    if scale is None:
+        scale = 1.0 / math.sqrt(K)
+    p = _make_params(q, k, v, g, beta, o, initial_state, final_state, scale, frame_tokens, flags)
+    with torch.cuda.device(q.device):
+        rc = lib.gdkvm_gdr_fwd(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        extra = f" (cudaError {lib.gdkvm_last_cuda_error()})" if rc == -7 else ""
+        raise RuntimeError(f"gdkvm_gdr_fwd: {_cabi.strerror(rc)}{extra}")
+
+
+@torch.library.impl("gdkvm::gdr_lkva", "CUDA")
+def _gdr_lkva_cuda(q, k, v, g, beta, scale=None, initial_state=None, output_final_state=True,
+                   frame_tokens=0, flags=0):
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    if initial_state is not None:
+        initial_state = initial_state.contiguous()
+    o = torch.empty((B, T, H, V), dtype=q.dtype, device=q.device)
+    sT = torch.empty((B, H, K, V) if output_final_state else (0,), dtype=torch.float32, device=q.device)
+    gdr_lkva_out(q, k, v, g, beta, o, sT if output_final_state else None, scale, initial_state,
+                 frame_tokens, flags)
+    return o, sT
+
+
+@torch.library.register_fake("gdkvm::gdr_lkva")
+def _gdr_lkva_fake(q, k, v, g, beta, scale=None, initial_state=None, output_final_state=True,
+                   frame_tokens=0, flags=0):
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    o = q.new_empty((B, T, H, V))
+    sT = q.new_empty((B, H, K, V) if output_final_state else (0,), dtype=torch.float32)
+    return o, sT
+
+
+def gdr_lkva(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, g: torch.Tensor, beta: torch.Tensor,
+             scale: Optional[float] = None, initial_state: Optional[torch.Tensor] = None,
+             output_final_state: bool = True, frame_tokens: int = 0,
+             flags: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """LKVA readout + GDR state update over a batch of clips on the current B200.
+
+    q,k [B,T,H,K]; v [B,T,H,V]; g (log-space gate) and beta [B,T,H]; initial_state fp32 [B,H,K,V].
+    Returns ``(o [B,T,H,V] in q.dtype, final_state fp32 [B,H,K,V] or None)``.
+    ``frame_tokens=C`` declares T = F*C with every frame one chunk (north_star).
+    """
+    o, sT = torch.ops.gdkvm.gdr_lkva(q, k, v, g, beta, scale, initial_state, output_final_state,
+                                     frame_tokens, flags)
+    return o, (sT if output_final_state else None)
+
+
+def chunk_gated_delta_rule(q, k, v, g, beta, scale=None, initial_state=None, output_final_state=False,
+                           **kwargs):
+    """Name- and argument-compatible alias of fla's entry point (fla/ops/gated_delta_rule/chunk.py:365)."""
+    unsupported = {kk: vv for kk, vv in kwargs.items()
+                   if kk not in ("frame_tokens", "flags") and vv is not None and vv is not False}
+    if unsupported:
+        raise NotImplementedError(f"gdkvm_b200.chunk_gated_delta_rule: unsupported arguments {sorted(unsupported)}")
+    return gdr_lkva(q, k, v, g, beta, scale, initial_state, output_final_state,
+                    kwargs.get("frame_tokens", 0), kwargs.get("flags", 0))
+
+
+def plan(q, k, v, g, beta, *, frame_tokens: int = 0, flags: int = 0) -> int:
+    """Which kernel the library would pick (0 recurrent, 1 tcgen05 chunked); needs no GPU."""
+    _check(q, k, v, g, beta, None)
+    o = v  # same geometry as the output
+    p = _make_params(q, k, v, g, beta, o, None, None, 1.0, frame_tokens, flags)
+    rc = _cabi.load().gdkvm_gdr_plan(ctypes.byref(p))
+    if rc < 0:
+        raise RuntimeError(f"gdkvm_gdr_plan: {_cabi.strerror(rc)}")
+    return rc
+
+
+def launch_count() -> int:
+    return _cabi.launch_count()

@@ -1,0 +1,118 @@
+/*
+ * gdkvm_gdr.h -- C ABI of the B200-native GDKVM memory op (LKVA readout + Gated Delta Rule).
+ *
+ * This is the drop-in boundary for the ONE hot path of wangrui2025/GDKVM named by BASELINE.json
+ * north_star.  The mounted reference exposes no code for it (reference README.md:1 "Code:
+ * github.com/wangrui2025/gdkvm_code", README.md:36-38 "Quick Start TBD"), so there is no reference
+ * FFI to bind; every entry point below instead replaces the reference *concept* cited next to it
+ * (README.md:20, website/src/content/homepage/en.json:20) with the call surface north_star fixes:
+ *     (q, k, v, gate, beta, initial_state) -> (readout, final_state)
+ * which is argument-compatible with flash-linear-attention's chunk_gated_delta_rule
+ * (fla/ops/gated_delta_rule/chunk.py:365-377), the op the upstream model most plausibly calls.
+ *
+ * Conventions: plain C, no torch/C++ types, caller-owned buffers, errors as negative ints (no
+ * exceptions cross the ABI), asynchronous on the caller's CUDA stream, CUDA-graph capturable
+ * (no host sync, no allocation after the first call on a device), re-entrant.
+ */
+#ifndef GDKVM_GDR_H_
+#define GDKVM_GDR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDKVM_ABI_VERSION 1
+
+/* element types of q/k/v/o (io_dtype) and of g/beta (gate_dtype) */
+enum GdkvmDtype { GDKVM_F32 = 0, GDKVM_BF16 = 1 };
+
+/* error codes (0 = success).  gdkvm_strerror() gives the text. */
+enum GdkvmStatus {
+    GDKVM_OK = 0,
+    GDKVM_ERR_NULL = -1,        /* a required pointer is NULL                               */
+    GDKVM_ERR_ABI = -2,         /* params->struct_size does not match this library          */
+    GDKVM_ERR_SHAPE = -3,       /* B/T/H/K/V/frame_tokens out of the supported set           */
+    GDKVM_ERR_DTYPE = -4,       /* unknown dtype enum                                        */
+    GDKVM_ERR_ALIGN = -5,       /* pointer/stride alignment not met                          */
+    GDKVM_ERR_ARCH = -6,        /* device is not sm_100 (no fallback is provided on purpose)  */
+    GDKVM_ERR_CUDA = -7,        /* a CUDA runtime/driver call failed (see gdkvm_last_cuda_error) */
+    GDKVM_ERR_UNSUPPORTED = -8  /* a forced path (flags) cannot run this problem             */
+};
+
+/* flags */
+#define GDKVM_FLAG_FORCE_RECURRENT 0x1u /* token-recurrent fp32 CUDA-core kernel (exact fp32 math)   */
+#define GDKVM_FLAG_FORCE_CHUNKED   0x2u /* tcgen05 WY/UT chunk kernel; error if the shape is not
+                                           covered instead of falling back                           */
+#define GDKVM_FLAG_FLAT_CHUNKS     0x4u /* chunked kernel: tile the flat token stream in 64-token
+                                           chunks instead of frame-aligned chunks (same results,
+                                           no 49->64 padding work)                                    */
+
+/*
+ * One forward call of the memory module over a batch of clips.
+ *   replaces: "Linear Key-Value Association ... state transition matrix; Gated Delta Rule ...
+ *   managing memory" (reference website/src/content/homepage/en.json:20; README.md:20).
+ *
+ * Per clip b and head h, tokens i = 0..T-1 in frame-major raster order, fp32 state S[K][V]:
+ *     S <- exp(g_i) S ;  r = v_i - S^T k_i ;  S <- S + k_i (beta_i r)^T ;  o_i = scale S^T q_i
+ *
+ * Tensors (strides in ELEMENTS; innermost K or V dimension contiguous):
+ *     q,k [B,T,H,K]   v,o [B,T,H,V]   g,beta [B,T,H]   initial/final state [B,H,K,V] fp32 contiguous
+ * stride arrays are {batch, token, head}.  frame_tokens = C > 0 declares T = F*C with every frame
+ * (C pixel tokens of one key/value feature map) forming one chunk; 0 = no frame structure.
+ */
+typedef struct GdkvmGdrParams {
+    uint32_t struct_size;        /* = sizeof(GdkvmGdrParams), ABI guard                       */
+    uint32_t flags;              /* GDKVM_FLAG_*                                              */
+    const void* q;
+    const void* k;
+    const void* v;
+    const void* g;               /* log-space gate (<= 0), one per token-head                 */
+    const void* beta;            /* write strength in (0,1)                                   */
+    const float* initial_state;  /* may be NULL (zero state)                                  */
+    void* o;                     /* readout, io_dtype                                         */
+    float* final_state;          /* may be NULL (not written)                                 */
+    int64_t q_stride[3];
+    int64_t k_stride[3];
+    int64_t v_stride[3];
+    int64_t o_stride[3];
+    int64_t g_stride[3];
+    int64_t beta_stride[3];
+    int32_t B, T, H, K, V;
+    int32_t frame_tokens;
+    int32_t io_dtype;            /* GdkvmDtype of q,k,v,o                                     */
+    int32_t gate_dtype;          /* GdkvmDtype of g,beta                                      */
+    float scale;                 /* readout scale; the Python op defaults it to K^-0.5        */
+    int32_t reserved;
+} GdkvmGdrParams;
+
+/* ABI version of the loaded library (compare with GDKVM_ABI_VERSION). */
+int gdkvm_abi_version(void);
+
+/* Static, never-NULL description of a GdkvmStatus. */
+const char* gdkvm_strerror(int status);
+
+/* cudaError_t of the most recent failing CUDA call on this thread (0 if none). */
+int gdkvm_last_cuda_error(void);
+
+/*
+ * Launch the forward op on `cuda_stream` (a cudaStream_t; NULL = legacy default stream) of the
+ * current device.  Returns immediately after enqueueing; 0 or a negative GdkvmStatus.
+ */
+int gdkvm_gdr_fwd(const GdkvmGdrParams* params, void* cuda_stream);
+
+/*
+ * Which kernel gdkvm_gdr_fwd would pick for `params` without launching anything:
+ * 0 = recurrent fp32 CUDA-core kernel, 1 = tcgen05 chunked kernel, negative = GdkvmStatus.
+ * Needs no GPU.
+ */
+int gdkvm_gdr_plan(const GdkvmGdrParams* params);
+
+/* Number of kernels this library has launched in the calling process (bench "gpu_launches"). */
+uint64_t gdkvm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GDKVM_GDR_H_ */

@@ -1,0 +1,175 @@
+"""CPU oracle for the GDKVM memory hot path (LKVA readout + Gated Delta Rule state update).
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``gdkvm_b200/`` may import this module; only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
+legs use it, and only as the checker (never as the thing shipped or measured as "ours").
+
+PARITY UNPINNED.  The mounted reference (``/root/reference``) contains no model code
+(``README.md:1`` points at a separate repo, ``README.md:36-38`` "Quick Start TBD"), no golden
+vectors and no numerical tests (``website/e2e/smoke.spec.ts:4-80`` are browser smoke tests), and
+the paper PDF is not mounted (``.MISSING_LARGE_BLOBS:1``).  This oracle is therefore written
+directly from the equations in ``BASELINE.json`` ``north_star`` / ``BASELINE.md`` §2, the only
+reference text naming the concept being ``README.md:20`` and
+``website/src/content/homepage/en.json:20``.  It is cross-checked (tests only, skip-if-missing)
+against flash-linear-attention 0.5.1 ``fla/ops/gated_delta_rule/naive.py:13`` (recurrent) and
+``:67`` (chunked), a third-party package that is *not* a reference pin.
+
+Semantics (per clip b, head h; state S in R^{K x V}, fp32):
+
+    for each token i in frame-major raster order:
+        S   <- exp(g_i) * S                       # alpha_i gate
+        r    = v_i - S^T k_i                      # delta-rule residual
+        S   <- S + k_i (beta_i * r)^T             # == alpha S (I - beta k k^T) + beta v k^T (transposed)
+        o_i  = scale * S^T q_i                    # LKVA readout, read-after-write
+
+Layout: q,k [B,T,H,K]; v,o [B,T,H,V]; g,beta [B,T,H]; initial/final state [B,H,K,V].
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+
+
+def _prep(q, k, v, g, beta, scale, initial_state):
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    assert q.shape == (B, T, H, K) and v.shape == (B, T, H, V)
+    assert g.shape == (B, T, H) and beta.shape == (B, T, H)
+    if scale is None:
+        scale = 1.0 / math.sqrt(K)
+    f = lambda x: x.detach().to("cpu", torch.float32)
+    q, k, v, g, beta = map(f, (q, k, v, g, beta))
+    if initial_state is None:
+        S = torch.zeros(B, H, K, V, dtype=torch.float32)
+    else:
+        assert initial_state.shape == (B, H, K, V)
+        S = f(initial_state).clone()
+    return q, k, v, g, beta, float(scale), S, (B, T, H, K, V)
+
+
+def gdr_recurrent_ref(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    g: torch.Tensor,
+    beta: torch.Tensor,
+    scale: Optional[float] = None,
+    initial_state: Optional[torch.Tensor] = None,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Token-recurrent ground truth, fp32 on CPU.
+
+    Follows BASELINE.md §2 line by line; one python iteration per token, vectorised over
+    (clip, head).  Returns ``(o [B,T,H,V] fp32, final_state [B,H,K,V] fp32)``.
+    """
+    q, k, v, g, beta, scale, S, (B, T, H, K, V) = _prep(q, k, v, g, beta, scale, initial_state)
+    o = torch.empty(B, T, H, V, dtype=torch.float32)
+    for i in range(T):
+        k_i = k[:, i]                                   # [B,H,K]
+        S = S * g[:, i].exp()[..., None, None]          # alpha gate
+        r = v[:, i] - torch.einsum("bhkv,bhk->bhv", S, k_i)
+        S = S + k_i[..., :, None] * (beta[:, i][..., None] * r)[..., None, :]
+        o[:, i] = scale * torch.einsum("bhkv,bhk->bhv", S, q[:, i])
+    return o, S
+
+
+def chunk_schedule(T: int, frame_tokens: int = 0, max_rows: int = 64):
+    """Chunk boundaries [(start, n_valid)] the kernel uses.
+
+    ``frame_tokens == 0``: tile the flat token stream in ``max_rows`` tokens.
+    ``frame_tokens == C``: every frame is one chunk, split in ``max_rows`` sub-chunks when
+    ``C > max_rows`` (CAMUS: 1024 tokens -> 16 x 64); a chunk never straddles two frames.
+    """
+    out = []
+    if T == 0:
+        return out
+    C = T if frame_tokens <= 0 else frame_tokens
+    assert T % C == 0, "T must be a whole number of frames"
+    for f0 in range(0, T, C):
+        for c0 in range(0, C, max_rows):
+            out.append((f0 + c0, min(max_rows, C - c0)))
+    return out
+
+
+def gdr_chunk_ref(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    g: torch.Tensor,
+    beta: torch.Tensor,
+    scale: Optional[float] = None,
+    initial_state: Optional[torch.Tensor] = None,
+    frame_tokens: int = 0,
+    max_rows: int = 64,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Chunked WY/UT restatement, fp32 on CPU.
+
+    Documents the math the sm_100a kernel executes; exactly equal to ``gdr_recurrent_ref`` in
+    exact arithmetic for any chunk schedule.  Per chunk with Gamma = cumsum(g):
+        A  = strict_tril(diag(beta) K K^T * exp(Gamma_i - Gamma_j));  T = (I + A)^-1
+        W  = T diag(beta) (K * exp(Gamma));   U = T diag(beta) V;      V_new = U - W S
+        O  = scale [ (Q * exp(Gamma)) S + tril(Q K^T * exp(Gamma_i - Gamma_j)) V_new ]
+        S <- exp(Gamma_last) S + (K * exp(Gamma_last - Gamma))^T V_new
+    """
+    q, k, v, g, beta, scale, S, (B, T, H, K, V) = _prep(q, k, v, g, beta, scale, initial_state)
+    o = torch.empty(B, T, H, V, dtype=torch.float32)
+    # work in [B,H,t,*]
+    qh, kh, vh = (x.permute(0, 2, 1, 3) for x in (q, k, v))
+    gh, bh = g.permute(0, 2, 1), beta.permute(0, 2, 1)
+    for (t0, n) in chunk_schedule(T, frame_tokens, max_rows):
+        sl = slice(t0, t0 + n)
+        Q, Kc, Vc = qh[:, :, sl], kh[:, :, sl], vh[:, :, sl]
+        G = gh[:, :, sl].cumsum(-1)                       # [B,H,n]
+        bt = bh[:, :, sl]
+        diff = G[..., :, None] - G[..., None, :]          # Gamma_i - Gamma_j
+        low = torch.tril(torch.ones(n, n, dtype=torch.bool))
+        decay = torch.where(low, diff, torch.full_like(diff, -float("inf"))).exp()   # mask before exp
+        KK = Kc @ Kc.transpose(-1, -2)
+        A = torch.tril(bt[..., :, None] * KK * decay, diagonal=-1)
+        eye = torch.eye(n, dtype=torch.float32).expand_as(A)
+        Tm = torch.linalg.solve_triangular(eye + A, eye.clone(), upper=False)
+        Kg = Kc * G.exp()[..., None]
+        W = Tm @ (bt[..., None] * Kg)
+        U = Tm @ (bt[..., None] * Vc)
+        Vn = U - W @ S
+        P = torch.tril((Q @ Kc.transpose(-1, -2)) * decay)
+        Oc = scale * ((Q * G.exp()[..., None]) @ S + P @ Vn)
+        o[:, sl] = Oc.permute(0, 2, 1, 3)
+        Gl = G[..., -1:]
+        S = Gl.exp()[..., None] * S + (Kc * (Gl - G).exp()[..., None]).transpose(-1, -2) @ Vn
+    return o, S
+
+
+def make_inputs(B, T, H, K, V, *, seed=1234, frame_tokens=0, correlated=False,
+                dtype=torch.float32, with_state=True):
+    """Seeded synthetic inputs of SURVEY.md §8(d) / BASELINE.md §3.
+
+    q,k = l2norm(randn); v = randn; beta = sigmoid(randn); g = logsigmoid(randn + 4);
+    S0 = 0.1 randn.  ``correlated=True`` draws one base key per frame and adds 0.3 randn
+    (adjacent pixels of one frame are highly correlated -- the hard case for the solve).
+    q,k,v are rounded to ``dtype`` (bf16 configs) so oracle and kernel see the same values.
+    """
+    gen = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=gen, dtype=torch.float32)
+    l2 = lambda x: x / x.norm(dim=-1, keepdim=True).clamp_min(1e-6)
+    q = l2(rn(B, T, H, K))
+    if correlated and frame_tokens > 0:
+        F = T // frame_tokens
+        base = rn(B, F, 1, H, K).expand(B, F, frame_tokens, H, K).reshape(B, T, H, K)
+        k = l2(base + 0.3 * rn(B, T, H, K))
+    else:
+        k = l2(rn(B, T, H, K))
+    v = rn(B, T, H, V)
+    beta = torch.sigmoid(rn(B, T, H))
+    g = torch.nn.functional.logsigmoid(rn(B, T, H) + 4.0)
+    S0 = 0.1 * rn(B, H, K, V) if with_state else None
+    q, k, v = (x.to(dtype) for x in (q, k, v))
+    return q, k, v, g, beta, S0
+
+
+def max_rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """Tolerance metric of BASELINE.md §2: max|a-b| / max|b| per tensor."""
+    a = a.detach().to("cpu", torch.float32)
+    b = b.detach().to("cpu", torch.float32)
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))

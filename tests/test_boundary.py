@@ -1,0 +1,136 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol the header
+declares, its struct matches the ctypes mirror, and validation/dispatch behave (no GPU compute)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gdkvm_gdr.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gdkvm_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(built_lib):
+    from gdkvm_b200 import _cabi
+    lib = ctypes.CDLL(built_lib)
+    names = _declared_functions()
+    assert set(names) == set(_cabi.EXPORTED_SYMBOLS)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/gdkvm_gdr.h but not exported"
+    assert lib.gdkvm_abi_version() == _cabi.GDKVM_ABI_VERSION
+
+
+def test_struct_layout_matches_header(built_lib, tmp_path):
+    """Compile a probe against the real header with gcc and compare size/offsets with ctypes."""
+    from gdkvm_b200 import _cabi
+    fields = [f[0] for f in _cabi.GdkvmGdrParams._fields_]
+    body = "".join(f'printf("{f} %zu\\n", offsetof(GdkvmGdrParams, {f}));' for f in fields)
+    c = tmp_path / "probe.c"
+    c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gdkvm_gdr.h"\n'
+                 'int main(void){printf("sizeof %zu\\n", sizeof(GdkvmGdrParams));' + body + 'return 0;}')
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
+    out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert int(out["sizeof"]) == ctypes.sizeof(_cabi.GdkvmGdrParams)
+    for f in fields:
+        assert int(out[f]) == getattr(_cabi.GdkvmGdrParams, f).offset, f
+
+
+def _inputs(B=2, T=98, H=2, K=64, V=256, dtype=torch.bfloat16):
+    from oracle.gdr_ref import make_inputs
+    return make_inputs(B, T, H, K, V, dtype=dtype)
+
+
+def test_plan_and_validation(built_lib):
+    import gdkvm_b200
+    from gdkvm_b200 import _cabi
+    from gdkvm_b200.ops import _make_params
+    q, k, v, g, beta, _ = _inputs()
+    assert gdkvm_b200.plan(q, k, v, g, beta, flags=_cabi.FLAG_FORCE_RECURRENT) == 0
+    assert gdkvm_b200.plan(q, k, v, g, beta, frame_tokens=49) in (0, 1)
+    lib = _cabi.load()
+
+    def rc_of(**over):
+        p = _make_params(q, k, v, g, beta, v, None, None, 1.0, over.pop("frame_tokens", 0), over.pop("flags", 0))
+        for kk, vv in over.items():
+            setattr(p, kk, vv)
+        return lib.gdkvm_gdr_plan(ctypes.byref(p))
+
+    assert rc_of(K=48) == -3                      # GDKVM_ERR_SHAPE
+    assert rc_of(frame_tokens=50) == -3           # T % frame_tokens != 0
+    assert rc_of(struct_size=8) == -2             # GDKVM_ERR_ABI
+    assert rc_of(io_dtype=7) == -4                # GDKVM_ERR_DTYPE
+    assert rc_of(q=q.data_ptr() + 2) == -5        # GDKVM_ERR_ALIGN
+    assert rc_of(q=None) == -1                    # GDKVM_ERR_NULL
+    assert rc_of(flags=3) == -8                   # both force flags
+    assert lib.gdkvm_gdr_plan(None) == -1
+    for code in range(0, -9, -1):
+        assert len(_cabi.strerror(code)) > 1
+    assert "unknown" in _cabi.strerror(-99)
+
+
+def test_fwd_without_gpu_fails_loudly(built_lib):
+    """No GPU here: the C entry point must return an error, never compute on the host."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from gdkvm_b200 import _cabi
+    from gdkvm_b200.ops import _make_params
+    q, k, v, g, beta, _ = _inputs(B=1, T=16, H=1)
+    o = torch.full_like(v, 7.0)
+    p = _make_params(q, k, v, g, beta, o, None, None, 1.0, 0, 0)
+    rc = _cabi.load().gdkvm_gdr_fwd(ctypes.byref(p), None)
+    assert rc in (-6, -7)                         # not sm_100 / CUDA error
+    assert torch.all(o == 7.0)                    # untouched
+
+
+def test_cpu_tensors_are_rejected(built_lib):
+    import gdkvm_b200
+    q, k, v, g, beta, _ = _inputs(B=1, T=16, H=1)
+    with pytest.raises(NotImplementedError):
+        gdkvm_b200.gdr_lkva(q, k, v, g, beta)
+    with pytest.raises(RuntimeError, match="no CPU implementation"):
+        gdkvm_b200.gdr_lkva_out(q, k, v, g, beta, torch.empty_like(v))
+
+
+def test_fake_impl_shapes(built_lib):
+    import gdkvm_b200  # noqa: F401
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    with FakeTensorMode():
+        q = torch.empty(3, 98, 4, 64, dtype=torch.bfloat16)
+        v = torch.empty(3, 98, 4, 256, dtype=torch.bfloat16)
+        g = torch.empty(3, 98, 4)
+        o, sT = torch.ops.gdkvm.gdr_lkva(q, q, v, g, g)
+        assert o.shape == (3, 98, 4, 256) and o.dtype == torch.bfloat16
+        assert sT.shape == (3, 4, 64, 256) and sT.dtype == torch.float32
+
+
+def test_argument_checks(built_lib):
+    import gdkvm_b200
+    q, k, v, g, beta, S0 = _inputs(B=1, T=16, H=1)
+    with pytest.raises(ValueError):
+        gdkvm_b200.plan(q, k[:, :8], v, g, beta)
+    with pytest.raises(TypeError):
+        gdkvm_b200.plan(q, k.float(), v, g, beta)
+    with pytest.raises(NotImplementedError):
+        gdkvm_b200.chunk_gated_delta_rule(q, k, v, g, beta, cu_seqlens=torch.tensor([0, 16]))
+
+
+def test_product_does_not_import_oracle():
+    """The shipped package must never route through the CPU oracle (or fla / triton)."""
+    pkg = os.path.join(ROOT, "gdkvm_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+(oracle|fla|triton)\b", src, flags=re.M), f
+    code = "import sys; import gdkvm_b200; assert not any(m.split('.')[0] in ('oracle','fla','triton') for m in sys.modules), 'leak'"
+    subprocess.check_call([sys.executable, "-c", code], cwd=ROOT)

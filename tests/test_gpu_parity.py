@@ -1,0 +1,215 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the torch.library op
+and the C ABI, against the CPU oracle on the same seeded inputs.
+
+Tolerances are BASELINE.json north_star's: max|a-b|/max|b| <= 1e-3 with fp32 I/O (fp32 state),
+<= 2e-2 with bf16 I/O, on the readout AND the final state.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.gdr_ref import gdr_recurrent_ref, make_inputs, max_rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2}
+RECURRENT, CHUNKED, FLAT = 0x1, 0x2, 0x4
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.fixture(scope="module")
+def op(built_lib):
+    assert torch.cuda.is_available(), "-m gpu tests need a B200"
+    import gdkvm_b200
+    return gdkvm_b200
+
+
+def _dev(*ts):
+    return [t.cuda() if t is not None else None for t in ts]
+
+
+def _run(op, q, k, v, g, beta, S0, **kw):
+    qd, kd, vd, gd, bd, sd = _dev(q, k, v, g, beta, S0)
+    o, sT = op.gdr_lkva(qd, kd, vd, gd, bd, kw.pop("scale", None), sd, True, **kw)
+    torch.cuda.synchronize()
+    return o.float().cpu(), sT.cpu()
+
+
+def _paths(op, q, k, v, g, beta, C):
+    """Every kernel path that can run this problem: forced recurrent, auto, and (if eligible) chunked."""
+    paths = [("recurrent", dict(flags=RECURRENT)), ("auto", dict(flags=0))]
+    if op.plan(q, k, v, g, beta, frame_tokens=C) == 1:
+        paths += [("chunked", dict(flags=CHUNKED)), ("chunked_flat", dict(flags=CHUNKED | FLAT))]
+    return paths
+
+
+@pytest.mark.parametrize("shape", [
+    # B, T, H, K, V, frame_tokens, correlated
+    (1, 32 * 49, 1, 64, 256, 49, False),     # BASELINE configs[0]
+    (2, 5 * 49, 3, 64, 256, 49, True),       # correlated keys inside a frame
+    (1, 2 * 1024, 2, 64, 256, 1024, True),   # CAMUS-shaped: 1024-token frames -> 16 sub-chunks
+    (2, 130, 2, 64, 128, 0, False),          # ragged tail (130 = 2*64 + 2)
+    (1, 37, 1, 32, 40, 0, False),            # K=32, V not a multiple of anything
+    (1, 70, 2, 128, 128, 0, False),          # K=128
+    (3, 1, 2, 64, 64, 0, False),             # single token
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_parity_vs_oracle(op, shape, dtype):
+    B, T, H, K, V, C, corr = shape
+    q, k, v, g, beta, S0 = make_inputs(B, T, H, K, V, seed=100 + T, frame_tokens=C, correlated=corr, dtype=dtype)
+    o_ref, s_ref = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    for name, kw in _paths(op, q, k, v, g, beta, C):
+        o, sT = _run(op, q, k, v, g, beta, S0, frame_tokens=C, **kw)
+        eo, es = max_rel_err(o, o_ref), max_rel_err(sT, s_ref)
+        assert eo <= TOL[dtype] and es <= TOL[dtype], (name, eo, es)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_fixtures(op, path):
+    z = np.load(path)
+    t = {n: torch.from_numpy(z[n]) for n in ("q", "k", "v", "g", "beta", "s0", "o", "sT")}
+    C = int(z["frame_tokens"])
+    for name, kw in _paths(op, t["q"], t["k"], t["v"], t["g"], t["beta"], C):
+        o, sT = _run(op, t["q"], t["k"], t["v"], t["g"], t["beta"], t["s0"], frame_tokens=C, **kw)
+        assert max_rel_err(o, t["o"]) <= 1e-3 and max_rel_err(sT, t["sT"]) <= 1e-3, name
+
+
+def test_recurrent_kernel_is_fp32_exact(op):
+    """The fp32 path follows the oracle operation for operation: far inside the 1e-3 contract."""
+    q, k, v, g, beta, S0 = make_inputs(2, 4 * 49, 2, 64, 256, seed=3, frame_tokens=49)
+    o_ref, s_ref = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    o, sT = _run(op, q, k, v, g, beta, S0, flags=RECURRENT)
+    assert max_rel_err(o, o_ref) < 2e-5 and max_rel_err(sT, s_ref) < 2e-5
+
+
+def test_zero_state_and_no_final_state(op):
+    q, k, v, g, beta, _ = make_inputs(1, 98, 2, 64, 128, seed=4, dtype=torch.bfloat16)
+    o_ref, _ = gdr_recurrent_ref(q, k, v, g, beta, 0.2, None)
+    qd, kd, vd, gd, bd = _dev(q, k, v, g, beta)
+    o, sT = op.gdr_lkva(qd, kd, vd, gd, bd, 0.2, None, False)
+    assert sT is None and max_rel_err(o, o_ref) <= 2e-2
+    o2, sT2 = op.chunk_gated_delta_rule(qd, kd, vd, gd, bd, scale=0.2, output_final_state=True)
+    assert torch.equal(o2, o) and sT2.shape == (1, 2, 64, 128)
+
+
+def test_empty_clip(op):
+    q, k, v, g, beta, S0 = make_inputs(2, 0, 2, 64, 64, seed=5)
+    o, sT = _run(op, q, k, v, g, beta, S0)
+    assert o.shape == (2, 0, 2, 64) and torch.equal(sT, S0)
+
+
+def test_bf16_gates(op):
+    q, k, v, g, beta, S0 = make_inputs(1, 98, 2, 64, 128, seed=6, dtype=torch.bfloat16)
+    g, beta = g.bfloat16(), beta.bfloat16()
+    o_ref, s_ref = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    o, sT = _run(op, q, k, v, g, beta, S0)
+    assert max_rel_err(o, o_ref) <= 2e-2 and max_rel_err(sT, s_ref) <= 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+def test_state_carry_and_strided_views(op, dtype):
+    """Two time segments (non-contiguous views of one clip batch) chained through final_state
+    reproduce the single call (row a5, BASELINE configs[3] streaming)."""
+    C = 49
+    q, k, v, g, beta, S0 = make_inputs(3, 6 * C, 2, 64, 256, seed=8, frame_tokens=C, dtype=dtype)
+    qd, kd, vd, gd, bd, sd = _dev(q, k, v, g, beta, S0)
+    for flags in (RECURRENT, 0):
+        o, sT = op.gdr_lkva(qd, kd, vd, gd, bd, None, sd, True, C, flags)
+        cut = 2 * C
+        oa, sa = op.gdr_lkva(qd[:, :cut], kd[:, :cut], vd[:, :cut], gd[:, :cut], bd[:, :cut], None, sd, True, C, flags)
+        ob, sb = op.gdr_lkva(qd[:, cut:], kd[:, cut:], vd[:, cut:], gd[:, cut:], bd[:, cut:], None, sa, True, C, flags)
+        assert torch.equal(torch.cat([oa, ob], 1), o), flags     # identical chunking => bit-identical
+        assert torch.equal(sb, sT), flags
+    mem = op.GDRMemory(frame_tokens=C)
+    o2, s2 = mem.forward_segments(qd, kd, vd, gd, bd, frames_per_segment=4, initial_state=sd)
+    o1, s1 = mem(qd, kd, vd, gd, bd, sd)
+    assert torch.equal(o2, o1) and torch.equal(s2, s1)
+
+
+def test_kat_on_device(op):
+    """Orthonormal keys, g=0, beta=1: S = sum k_i v_i^T exactly; reading q=k_j returns scale*v_j."""
+    K, V = 64, 64
+    keys = torch.eye(K)[None, :, None, :].contiguous()
+    vals = torch.arange(K * V, dtype=torch.float32).reshape(1, K, 1, V) / 64.0
+    for flags in (RECURRENT, 0):
+        o, S = _run(op, keys, keys, vals, torch.zeros(1, K, 1), torch.ones(1, K, 1), None, scale=0.5, flags=flags)
+        assert max_rel_err(S[0, 0], vals[0, :, 0]) < 1e-3
+        assert max_rel_err(o, 0.5 * vals) < 1e-3
+
+
+def test_errors_are_loud(op):
+    q, k, v, g, beta, S0 = _dev(*make_inputs(1, 16, 1, 64, 64, seed=1))
+    with pytest.raises(RuntimeError, match="unsupported shape"):
+        op.gdr_lkva(q[..., :48].contiguous(), k[..., :48].contiguous(), v, g, beta)
+    with pytest.raises(RuntimeError, match="unsupported shape"):
+        op.gdr_lkva(q, k, v, g, beta, frame_tokens=5)
+    with pytest.raises(ValueError):
+        op.gdr_lkva(q, k, v, g, beta, None, S0[..., :32])
+
+
+def test_host_pipeline_matches_device_call(op):
+    from gdkvm_b200.host import gdr_lkva_host
+    q, k, v, g, beta, S0 = make_inputs(5, 3 * 49, 2, 64, 256, seed=12, frame_tokens=49, dtype=torch.bfloat16)
+    pin = lambda t: t.pin_memory()
+    o_h, s_h = gdr_lkva_host(pin(q), pin(k), pin(v), pin(g), pin(beta), None, pin(S0), 49, clips_per_group=2)
+    o, sT = _run(op, q, k, v, g, beta, S0, frame_tokens=49)
+    assert torch.equal(o_h.float(), o) and torch.equal(s_h, sT)
+
+
+# ---------------- full-size (BASELINE configs[1]) properties ----------------
+
+@pytest.fixture(scope="module")
+def echonet_batch():
+    """configs[1]: 64 clips x 128 frames x 49 tokens, 8 heads, K=64, V=256, bf16 -- built on the GPU."""
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    B, T, H, K, V = 64, 128 * 49, 8, 64, 256
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda", dtype=torch.float32)
+    l2 = lambda x: torch.nn.functional.normalize(x, dim=-1)
+    q = l2(rn(B, T, H, K)).bfloat16()
+    k = l2(rn(B, T, H, K)).bfloat16()
+    v = rn(B, T, H, V).bfloat16()
+    beta = torch.sigmoid(rn(B, T, H))
+    gate = torch.nn.functional.logsigmoid(rn(B, T, H) + 4.0)
+    S0 = 0.1 * rn(B, H, K, V)
+    return q, k, v, gate, beta, S0
+
+
+def test_full_size_sample_vs_oracle(op, echonet_batch, c_oracle):
+    """Whole configs[1] batch on the GPU; 2 clips x 8 heads checked against the C oracle."""
+    q, k, v, g, beta, S0 = echonet_batch
+    o, sT = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 49)
+    torch.cuda.synchronize()
+    for b in (0, 63):
+        sl = slice(b, b + 1)
+        o_ref, s_ref = c_oracle.gdr_recurrent_c(q[sl].cpu(), k[sl].cpu(), v[sl].cpu(), g[sl].cpu(),
+                                                beta[sl].cpu(), None, S0[sl].cpu())
+        assert max_rel_err(o[sl], o_ref) <= 2e-2 and max_rel_err(sT[sl], s_ref) <= 2e-2
+
+
+def test_full_size_linearity(op, echonet_batch):
+    """(v, S0) -> (o, S_T) is linear; scaling by 2 is exact in binary floating point, so the
+    full-size outputs must scale bit-exactly -- a size-independent check of every chain."""
+    q, k, v, g, beta, S0 = echonet_batch
+    o, sT = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 49)
+    o2, sT2 = op.gdr_lkva(q, k, v * 2, g, beta, None, S0 * 2, True, 49)
+    assert torch.equal(o2.float(), o.float() * 2) and torch.equal(sT2, sT * 2)
+
+
+def test_full_size_state_carry(op, echonet_batch):
+    q, k, v, g, beta, S0 = echonet_batch
+    o, sT = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 49)
+    cut = 64 * 49
+    oa, sa = op.gdr_lkva(q[:, :cut], k[:, :cut], v[:, :cut], g[:, :cut], beta[:, :cut], None, S0, True, 49)
+    ob, sb = op.gdr_lkva(q[:, cut:], k[:, cut:], v[:, cut:], g[:, cut:], beta[:, cut:], None, sa, True, 49)
+    assert torch.equal(oa, o[:, :cut]) and torch.equal(ob, o[:, cut:]) and torch.equal(sb, sT)
+
+
+def test_full_size_paths_agree(op, echonet_batch):
+    """Recurrent fp32 kernel vs the default path over the whole batch (chunk-size invariance)."""
+    q, k, v, g, beta, S0 = echonet_batch
+    o, sT = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 49)
+    o_r, s_r = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 49, RECURRENT)
+    assert max_rel_err(o, o_r) <= 2e-2 and max_rel_err(sT, s_r) <= 2e-2

@@ -1,0 +1,145 @@
+"""CPU tests of the oracle (no GPU): self-consistency, golden vectors, known answers.
+
+Model: the test pyramid SURVEY.md section 4/7 asks for, since the reference ships no numerical tests.
+"""
+import glob
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.gdr_ref import (chunk_schedule, gdr_chunk_ref, gdr_recurrent_ref, make_inputs, max_rel_err)
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _load(path):
+    z = np.load(path)
+    t = {k: torch.from_numpy(z[k]) for k in ("q", "k", "v", "g", "beta", "s0", "o", "sT")}
+    return t, int(z["frame_tokens"])
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_recurrent(path):
+    t, _ = _load(path)
+    o, sT = gdr_recurrent_ref(t["q"], t["k"], t["v"], t["g"], t["beta"], None, t["s0"])
+    assert max_rel_err(o, t["o"]) < 1e-5
+    assert max_rel_err(sT, t["sT"]) < 1e-5
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_chunked_and_c_port(path, c_oracle):
+    t, C = _load(path)
+    o, sT = gdr_chunk_ref(t["q"], t["k"], t["v"], t["g"], t["beta"], None, t["s0"], frame_tokens=C)
+    assert max_rel_err(o, t["o"]) < 2e-5 and max_rel_err(sT, t["sT"]) < 2e-5
+    o, sT = c_oracle.gdr_recurrent_c(t["q"], t["k"], t["v"], t["g"], t["beta"], None, t["s0"])
+    assert max_rel_err(o, t["o"]) < 1e-5 and max_rel_err(sT, t["sT"]) < 1e-5
+
+
+def test_golden_present():
+    assert len(GOLDEN) >= 4
+
+
+def test_fla_naive_cross_check():
+    """Independent third-party restatement (not a reference pin); skipped where fla is absent."""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        naive = pytest.importorskip("fla.ops.gated_delta_rule.naive")
+    q, k, v, g, beta, S0 = make_inputs(2, 2 * 49, 2, 64, 96, seed=5, frame_tokens=49)
+    o, sT = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    of, sf = naive.naive_recurrent_gated_delta_rule(q, k, v, beta, g, initial_state=S0.clone(),
+                                                    output_final_state=True)
+    oc, sc = naive.naive_chunk_gated_delta_rule(q, k, v, g, beta, chunk_size=49, initial_state=S0.clone(),
+                                                output_final_state=True)
+    assert max_rel_err(o, of) < 1e-5 and max_rel_err(sT, sf) < 1e-5
+    assert max_rel_err(o, oc) < 1e-5 and max_rel_err(sT, sc) < 1e-5
+
+
+@pytest.mark.parametrize("frame_tokens,max_rows", [(49, 64), (0, 64), (0, 16), (256, 64), (49, 49), (0, 1)])
+def test_chunk_equals_recurrent(frame_tokens, max_rows):
+    T = 512 if frame_tokens == 256 else 3 * 49
+    q, k, v, g, beta, S0 = make_inputs(2, T, 2, 32, 48, seed=7, frame_tokens=frame_tokens, correlated=frame_tokens > 0)
+    o1, s1 = gdr_recurrent_ref(q, k, v, g, beta, 0.37, S0)
+    o2, s2 = gdr_chunk_ref(q, k, v, g, beta, 0.37, S0, frame_tokens=frame_tokens, max_rows=max_rows)
+    assert max_rel_err(o2, o1) < 2e-5 and max_rel_err(s2, s1) < 2e-5
+
+
+def test_chunk_schedule():
+    assert chunk_schedule(98, 49) == [(0, 49), (49, 49)]
+    assert chunk_schedule(130, 0) == [(0, 64), (64, 64), (128, 2)]
+    assert chunk_schedule(2048, 1024)[:3] == [(0, 64), (64, 64), (128, 64)] and len(chunk_schedule(2048, 1024)) == 32
+    assert chunk_schedule(0, 0) == []
+
+
+def test_state_carry_split():
+    """F frames in one call == two calls chained through final_state (row a5)."""
+    q, k, v, g, beta, S0 = make_inputs(2, 6 * 49, 2, 64, 64, seed=9, frame_tokens=49)
+    o, sT = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    cut = 2 * 49
+    oa, sa = gdr_recurrent_ref(q[:, :cut], k[:, :cut], v[:, :cut], g[:, :cut], beta[:, :cut], None, S0)
+    ob, sb = gdr_recurrent_ref(q[:, cut:], k[:, cut:], v[:, cut:], g[:, cut:], beta[:, cut:], None, sa)
+    assert torch.equal(torch.cat([oa, ob], 1), o) and torch.equal(sb, sT)
+
+
+def test_pad_tokens_are_noops():
+    """k=0, beta=0, g=0 tokens leave the state untouched (what the kernel's 49->64 padding relies on)."""
+    q, k, v, g, beta, S0 = make_inputs(1, 20, 1, 32, 16, seed=3)
+    o, sT = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    pad = lambda x, val=0.0: torch.cat([x, torch.full((1, 5) + tuple(x.shape[2:]), val)], 1)
+    o2, sT2 = gdr_recurrent_ref(pad(q), pad(k), pad(v, 3.0), pad(g), pad(beta), None, S0)
+    assert torch.equal(o2[:, :20], o) and torch.equal(sT2, sT)
+
+
+# ---- analytic known-answer tests ----
+
+def test_kat_delta_rule_overwrites():
+    """g=0, beta=1, |k|=1: after writing (k, v), S^T k == v exactly."""
+    torch.manual_seed(0)
+    K, V = 16, 8
+    k = torch.nn.functional.normalize(torch.randn(1, 1, 1, K), dim=-1)
+    v = torch.randn(1, 1, 1, V)
+    S0 = torch.randn(1, 1, K, V)
+    _, S = gdr_recurrent_ref(k, k, v, torch.zeros(1, 1, 1), torch.ones(1, 1, 1), 1.0, S0)
+    assert torch.allclose(torch.einsum("kv,k->v", S[0, 0], k[0, 0, 0]), v[0, 0, 0], atol=1e-5)
+
+
+def test_kat_beta_zero_is_pure_decay():
+    q, k, v, g, beta, S0 = make_inputs(1, 7, 2, 16, 8, seed=2)
+    _, S = gdr_recurrent_ref(q, k, v, g, torch.zeros_like(beta), None, S0)
+    expect = S0 * g.sum(1).exp()[..., None, None]
+    assert torch.allclose(S, expect, rtol=1e-5, atol=1e-7)
+
+
+def test_kat_orthonormal_keys():
+    """Orthonormal keys, g=0, beta=1, S0=0: S = sum_i k_i v_i^T and reading q=k_j returns scale*v_j."""
+    K, V = 8, 4
+    keys = torch.eye(K)[None, :, None, :]                       # [1,K,1,K]
+    vals = torch.arange(K * V, dtype=torch.float32).reshape(1, K, 1, V)
+    o, S = gdr_recurrent_ref(keys, keys, vals, torch.zeros(1, K, 1), torch.ones(1, K, 1), 0.5, None)
+    assert torch.equal(S[0, 0], vals[0, :, 0])
+    assert torch.equal(o, 0.5 * vals)                            # read-after-write, token causal
+
+
+def test_kat_hand_computed():
+    """K=2, V=2, T=3 worked by hand from the recurrence (alpha=0.5 on token 1)."""
+    q = torch.tensor([[1., 0.], [0., 1.], [1., 1.]]).reshape(1, 3, 1, 2)
+    k = torch.tensor([[1., 0.], [0., 1.], [1., 0.]]).reshape(1, 3, 1, 2)
+    v = torch.tensor([[2., 4.], [6., 8.], [1., 1.]]).reshape(1, 3, 1, 2)
+    g = torch.tensor([0., np.log(0.5), 0.]).reshape(1, 3, 1)
+    beta = torch.tensor([1., 0.5, 1.]).reshape(1, 3, 1)
+    o, S = gdr_recurrent_ref(q, k, v, g, beta, 1.0, None)
+    # t0: S=[[2,4],[0,0]], o=[2,4]
+    # t1: S*=.5 -> [[1,2],[0,0]]; r=.5*([6,8]-[0,0])=[3,4]; S=[[1,2],[3,4]]; o=S^T[0,1]=[3,4]
+    # t2: r=[1,1]-[1,2]=[0,-1]; S=[[1,1],[3,4]]; o=S^T[1,1]=[4,5]
+    assert torch.allclose(o[0, :, 0], torch.tensor([[2., 4.], [3., 4.], [4., 5.]]), atol=1e-6)
+    assert torch.allclose(S[0, 0], torch.tensor([[1., 1.], [3., 4.]]), atol=1e-6)
+
+
+def test_linearity_in_values():
+    """The map (v, S0) -> (o, S_T) is linear: scaling both by 2 scales the outputs by exactly 2."""
+    q, k, v, g, beta, S0 = make_inputs(1, 50, 1, 16, 8, seed=4)
+    o, S = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    o2, S2 = gdr_recurrent_ref(q, k, 2 * v, g, beta, None, 2 * S0)
+    assert torch.equal(o2, 2 * o) and torch.equal(S2, 2 * S)
