@@ -114,8 +114,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                  const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mo,
                  const GdkvmGdrParams p, const int C, const int F) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-align inside the shared window with pointer arithmetic only (an integer round trip would
+    // demote every access below from LDS/STS to generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     float* sA = reinterpret_cast<float*>(smem + kOffA);
     float* sY = reinterpret_cast<float*>(smem + kOffY);
