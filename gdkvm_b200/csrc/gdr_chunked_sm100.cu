@@ -1,4 +1,4 @@
-// Chunked (WY/UT) GDR/LKVA kernel on the 5th-gen tensor cores of sm_100a.
+// Chunked (WY/UT) GDR/LKVA kernel on the 5th-gen tensor cores of sm_100a -- warp-specialised.
 //
 // One CTA = one (clip, head) chain, all V value columns, 64-token chunks (a frame is one chunk;
 // frames longer than 64 tokens are cut into 64-token sub-chunks, shorter ones are zero-padded by
@@ -9,16 +9,29 @@
 //     Vn^T = V^T T'^T - Sb W^T           (Sb = bf16 copy of S^T, TMEM A-operand)
 //     O^T  = Sb Q~^T + Vnb P^T           (Vnb = bf16 copy of Vn^T, TMEM A-operand, aliases Vn)
 //     S^T  = gamma S^T + Vnb K'          (fp32 accumulate in place)
-// with the state-independent ("K-side") operands built per chunk:
-//     [K;Q] K^T -> gate/mask -> A (fp32), P (bf16);  T = (I + A)^-1 in fp32 on CUDA cores
-//     (16x16 forward substitution + two block-merge levels);  T' = T diag(beta);
-//     W^T = K~^T T'^T via one more MMA;  K~ = K e^Gamma, K' = K e^(Gamma_last - Gamma),
-//     Q~ = scale Q e^Gamma are in-place row scalings of the TMA tiles (swizzle-agnostic).
-// Every contraction is a 128 x 64 x 64 tcgen05.mma (bf16 in, fp32 TMEM accumulate); q/k/v tiles
-// arrive by TMA (128B swizzle, next chunk prefetched while the current one is computed) and the
-// readout leaves through a TMA store.  Layout facts used here were verified on hardware by
-// tests/probes/umma_probe.cu.
+// Every contraction is a 128 x 64 x 64 tcgen05.mma (bf16 in, fp32 TMEM accumulate).
 //
+// Roles (18 warps):
+//   warps 0-7   K-side group: everything that does not depend on the state, one chunk AHEAD of the
+//               state side: [K;Q]K^T accumulators -> masked/gated A (fp32) and P (bf16); the
+//               triangular inverse (I + A)^-1 in fp32-grade arithmetic (16x16 forward substitution on
+//               CUDA cores, block merges as 3xTF32 mma.sync); T' = T diag(..) ; W^T ; the in-place row
+//               scalings K~, Q~ and K' of the TMA tiles (the 128B swizzle keeps rows intact).
+//   warps 8-11 / 12-15   state warpgroups, one per 128 value columns: S -> (Sb, gamma S), Vn -> Vnb,
+//               readout O -> bf16 -> staging -> TMA store; initial / final state.
+//   warp 16     issuer K: TMA loads (q, k, v tiles, one chunk of prefetch) and the K-side MMAs.
+//   warp 17     issuer S: the five state-side MMAs per value half.
+// The roles meet only through mbarriers (tcgen05.commit / arrive), so the K-side work of chunk n+1,
+// the state-side work of chunk n and the TMA traffic of chunk n+2 overlap.
+//
+// "f-folded" gating (fast path, chunk decay > e^-60): with e_i = exp(Gamma_i), f_j = exp(-Gamma_j)
+//     T = diag(e) X diag(f),  X = (I + strict_tril(beta_i k_i.k_j))^-1   (no decay inside the solve)
+// and the chunk is carried in the scaled variable V^_j = f_j Vnew_j, which turns every decay factor
+// into a row / column scaling:  T' = X diag(f beta), P = scale e_i (q_i.k_j)[j<=i], K' = gamma K.
+// Chunks with stronger decay use the per-element exp(Gamma_i - Gamma_j) form (slow path); both
+// produce the same five operands, so the MMA sequence is identical.
+//
+// Layout facts used here were verified on hardware by tests/probes/umma_probe.cu.
 // Math: oracle/gdr_ref.py::gdr_chunk_ref.
 #include <mutex>
 
@@ -31,23 +44,28 @@ namespace {
 
 using namespace sm100;
 
-constexpr int kThreads = 256;
-constexpr int kPitchA = 68;   // fp32 pitch of the 64x64 solve matrix (16B-aligned rows, conflict-free v4 stores)
-constexpr int kPitchY = 36;
+constexpr int kKThreads = 256;                 // K-side group
+constexpr int kThreads = 18 * 32;              // whole CTA
+constexpr int kPitchA = 68;   // fp32 pitch of the 64x64 solve matrix: conflict-free mma A-fragment loads
+constexpr int kPitchY = 40;   // pitch of the merge scratch: conflict-free mma B-fragment loads
 
 // ---- shared memory map (bytes from a 1024-aligned base) ----
 constexpr uint32_t kStageBytes = 49152;          // Kt 8K | Qt 8K | Vt 32K   (Qt must follow Kt: stacked [K;Q] operand)
 constexpr uint32_t kOffKt = 0, kOffQt = 8192, kOffVt = 16384;
-constexpr uint32_t kOffKp = 2 * kStageBytes;     // K'  (B of the state update, MN-major)
-constexpr uint32_t kOffTp = kOffKp + 8192;       // T'  (B of U / W, K-major)
-constexpr uint32_t kOffPp = kOffTp + 8192;       // P   (B of the intra-chunk readout, K-major)
-constexpr uint32_t kOffWt = kOffPp + 8192;       // W^T (B of the state correction, MN-major)
-constexpr uint32_t kOffOst = kOffWt + 8192;      // readout staging for the TMA store, [V/64][64 tok][64] bf16
+constexpr uint32_t kOffKp = 2 * kStageBytes;     // K'  [2]  (B of the state update, MN-major)
+constexpr uint32_t kOffPp = kOffKp + 16384;      // P   [2]  (B of the intra-chunk readout, K-major)
+constexpr uint32_t kOffWt = kOffPp + 16384;      // W^T [2]  (B of the state correction, MN-major)
+constexpr uint32_t kOffTp = kOffWt + 16384;      // T'  [2]  (B of U / W, K-major)
+constexpr uint32_t kOffOst = kOffTp + 16384;     // readout staging, per value half [2][64 tok][64] bf16
 constexpr uint32_t kOffA = kOffOst + 32768;      // fp32 solve matrix
 constexpr uint32_t kOffY = kOffA + 64 * kPitchA * 4;
-constexpr uint32_t kOffF = kOffY + 32 * kPitchY * 4;   // floats: g[2][64] beta[2][64] Gam[64] E[64] Fi[64] Kd[64] scal[4]
-constexpr uint32_t kOffBar = kOffF + (8 * 64 + 4) * 4;
-constexpr uint32_t kSmemBytes = kOffBar + 64 + 1024;   // + alignment slack
+constexpr uint32_t kOffF = kOffY + 32 * kPitchY * 4;
+//   floats: g[2][64] beta[2][64] Gam[64] E[64] Cj[64] Kd[64] gamma[2] fast[1] pad[1]
+constexpr uint32_t kNumFloats = 8 * 64 + 4;
+constexpr uint32_t kOffBar = kOffF + kNumFloats * 4;
+constexpr uint32_t kNumBars = 24;
+constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;   // + tmem slot + alignment slack
+static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
 // ---- tensor memory map (columns) ----
 constexpr uint32_t kColS = 0;      // S^T   [h]: +64h   fp32
@@ -57,6 +75,27 @@ constexpr uint32_t kColSb = 384;   // Sb    [h]: +32h   bf16 x2 per column
 constexpr uint32_t kColKQ = 448;   // [K;Q]K^T, later W^T (64 columns)
 constexpr uint32_t kTmemCols = 512;
 
+// ---- mbarrier slots ----
+enum Bar : int {
+    kTmaFull = 0,    // [2] tiles of a chunk landed                      (tx)      -> issuer K, K group
+    kKqFull = 2,     //     [K;Q]K^T accumulators complete                (commit)  -> K group
+    kTpReady = 3,    // [2] T' (and K~, Q~, K', P) written                (1)       -> issuer K (W), issuer S (U)
+    kWFull = 5,      //     W^T accumulators complete                     (commit)  -> K group
+    kKsideFull = 6,  // [2] W^T operand + gamma published (K side done)   (1)       -> issuer K/S, state groups
+    kKsideEmpty = 8, // [2] every MMA of the chunk completed              (commit)  -> K group (operand buffers free)
+    kD1Done = 10,    //     tile stage no longer read by any MMA          (commit)  -> issuer K (TMA refill)
+    kSbReady = 11,   // [2] per half: Sb + decayed S in TMEM              (128)     -> issuer S
+    kVnFull = 13,    // [2] per half: Vn^T complete                       (commit)  -> state group
+    kVnbReady = 15,  // [2] per half: Vnb in TMEM                         (128)     -> issuer S
+    kSReady = 17,    // [2] per half: state update complete               (commit)  -> state group
+    kOFull = 19,     // [2] per half: readout accumulators complete       (commit)  -> state group
+    kOFree = 21,     // [2] per half: readout accumulators drained        (128)     -> issuer S
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ uint32_t scale_bf16x2(uint32_t w, float s) {
     const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
     return pack_bf16(lo * s, hi * s);
@@ -65,49 +104,60 @@ __device__ __forceinline__ uint4 scale_row8(uint4 v, float s) {
     return make_uint4(scale_bf16x2(v.x, s), scale_bf16x2(v.y, s), scale_bf16x2(v.z, s), scale_bf16x2(v.w, s));
 }
 
+// ---- 3xTF32 warp MMA: fp32-grade 16x8 += 16x8k * 8kx8 on the legacy tensor path (tiny, K-side only) ----
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// c(16x8) += A[0..15][kbeg..kend) * B[kbeg..kend)[0..7];  A row-major pitch pa, B row-major pitch pb
+__device__ __forceinline__ void tile_mma_3xtf32(float (&c)[4], const float* A, int pa, const float* B, int pb,
+                                                int kbeg, int kend, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    for (int k0 = kbeg; k0 < kend; k0 += 8) {
+        const float af[4] = {A[g * pa + k0 + t], A[(g + 8) * pa + k0 + t], A[g * pa + k0 + t + 4], A[(g + 8) * pa + k0 + t + 4]};
+        const float bf[2] = {B[(k0 + t) * pb + g], B[(k0 + t + 4) * pb + g]};
+        uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ah[i] = to_tf32(af[i]); al[i] = to_tf32(af[i] - __uint_as_float(ah[i])); }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) { bh[i] = to_tf32(bf[i]); bl[i] = to_tf32(bf[i] - __uint_as_float(bh[i])); }
+        mma_tf32(c, al, bh);
+        mma_tf32(c, ah, bl);
+        mma_tf32(c, ah, bh);
+    }
+}
+
 // X21 <- -X22 (L21 X11) for NP independent pairs of adjacent N x N diagonal blocks of the unit
-// lower-triangular matrix held in sA (in place; sY is scratch).  All 256 threads participate.
+// lower-triangular matrix held in sA (in place; sY is scratch).  Called by the whole K group.
 template <int N, int NP>
-__device__ __forceinline__ void tri_merge(float* sA, float* sY, int tid) {
-    constexpr int JW = N * N * NP / kThreads;   // outputs per thread, contiguous along j
-    constexpr int TPP = kThreads / NP;          // threads per pair
-    constexpr int TPR = N / JW;                 // threads per output row
-    const int pair = tid / TPP, t = tid % TPP;
-    const int i = t / TPR, j0 = (t % TPR) * JW;
+__device__ __forceinline__ void tri_merge(float* sA, float* sY, int warp, int lane) {
+    constexpr int NT = N / 8, TPP = (N / 16) * NT, TILES = NP * TPP;
+    const int g = lane >> 2, t = lane & 3;
+    const int pair = warp / TPP, tile = warp % TPP, mt = tile / NT, nt = tile % NT;
     const int o1 = pair * 2 * N, o2 = o1 + N;
-    const float* L21 = sA + o2 * kPitchA + o1;
-    const float* X11 = sA + o1 * kPitchA + o1;
-    const float* X22 = sA + o2 * kPitchA + o2;
     float* Y = sY + pair * (N * kPitchY);
-    float acc[JW];
-#pragma unroll
-    for (int jj = 0; jj < JW; ++jj) acc[jj] = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < N; k += 4) {
-        const float4 a = *reinterpret_cast<const float4*>(L21 + i * kPitchA + k);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-            for (int jj = 0; jj < JW; ++jj) acc[jj] = fmaf(av[kk], X11[(k + kk) * kPitchA + j0 + jj], acc[jj]);
+    if (warp < TILES) {      // Y = L21 X11   (X11 lower triangular: rows k < 8 nt contribute nothing)
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        tile_mma_3xtf32(c, sA + (o2 + mt * 16) * kPitchA + o1, kPitchA, sA + o1 * kPitchA + o1 + nt * 8, kPitchA, nt * 8, N, lane);
+        *reinterpret_cast<float2*>(Y + (mt * 16 + g) * kPitchY + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
+        *reinterpret_cast<float2*>(Y + (mt * 16 + g + 8) * kPitchY + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
     }
-#pragma unroll
-    for (int jj = 0; jj < JW; ++jj) Y[i * kPitchY + j0 + jj] = acc[jj];
-    __syncthreads();
-#pragma unroll
-    for (int jj = 0; jj < JW; ++jj) acc[jj] = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < N; k += 4) {
-        const float4 a = *reinterpret_cast<const float4*>(X22 + i * kPitchA + k);
-        const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-            for (int jj = 0; jj < JW; ++jj) acc[jj] = fmaf(av[kk], Y[(k + kk) * kPitchY + j0 + jj], acc[jj]);
+    named_bar_sync(1, kKThreads);
+    if (warp < TILES) {      // X21 = -X22 Y  (X22 lower triangular: columns k > row contribute nothing)
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        tile_mma_3xtf32(c, sA + (o2 + mt * 16) * kPitchA + o2, kPitchA, Y + nt * 8, kPitchY, 0, mt * 16 + 16, lane);
+        float* X21 = sA + (o2 + mt * 16) * kPitchA + o1 + nt * 8 + 2 * t;
+        *reinterpret_cast<float2*>(X21 + g * kPitchA) = make_float2(-c[0], -c[1]);
+        *reinterpret_cast<float2*>(X21 + (g + 8) * kPitchA) = make_float2(-c[2], -c[3]);
     }
-#pragma unroll
-    for (int jj = 0; jj < JW; ++jj) sA[(o2 + i) * kPitchA + o1 + j0 + jj] = -acc[jj];
-    __syncthreads();
+    named_bar_sync(1, kKThreads);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -121,366 +171,418 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     const uint32_t sbase = smem_u32(smem);
     float* sA = reinterpret_cast<float*>(smem + kOffA);
     float* sY = reinterpret_cast<float*>(smem + kOffY);
-    float* sG = reinterpret_cast<float*>(smem + kOffF);   // [2][64]
-    float* sBt = sG + 128;                                // [2][64]
+    float* sG = reinterpret_cast<float*>(smem + kOffF);   // [2][64] log gates of the chunk in each stage
+    float* sBt = sG + 128;                                // [2][64] beta
     float* sGam = sBt + 128;                              // Gamma_i (inclusive cumsum of g)
     float* sE = sGam + 64;                                // exp(Gamma_i)
-    float* sFi = sE + 64;                                 // exp(-Gamma_i)   (fast path only)
-    float* sKd = sFi + 64;                                // exp(Gamma_last - Gamma_i)
-    float* sScal = sKd + 64;                              // [0] exp(Gamma_last)  [1] fast-path flag
-    uint64_t* bar_tma = reinterpret_cast<uint64_t*>(smem + kOffBar);   // [2]
-    uint64_t* bar_mma = bar_tma + 2;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    float* sCj = sE + 64;                                 // column factor of T': f_j beta_j (fast) | beta_j (slow)
+    float* sKd = sCj + 64;                                // row factor of K':    gamma (fast) | exp(Gamma_last - Gamma_i) (slow)
+    float* sGamma = sKd + 64;                             // [2] exp(Gamma_last) of the chunk in each stage
+    float* sFast = sGamma + 2;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int wq = warp & 3, wh = warp >> 2;     // TMEM lane quadrant, value half
     const int chain = blockIdx.x, b = chain / p.H, h = chain % p.H;
     const int V = p.V, NH = V >> 7, VB = V >> 6;
     const int cpf = (C + 63) >> 6, NC = F * cpf;
-    const bool state_warp = wh < NH;
     const float scale = p.scale;
-    const int64_t g_off = (int64_t)b * p.g_stride[0] + (int64_t)h * p.g_stride[2];
-    const int64_t bt_off = (int64_t)b * p.beta_stride[0] + (int64_t)h * p.beta_stride[2];
-    const uint32_t stage_tx = 16384u + (uint32_t)VB * 8192u;
 
     if (tid == 0) {
-        mbar_init(&bar_tma[0], 1); mbar_init(&bar_tma[1], 1); mbar_init(bar_mma, 1);
+        mbar_init(&bars[kTmaFull], 1); mbar_init(&bars[kTmaFull + 1], 1);
+        mbar_init(&bars[kKqFull], 1);
+        mbar_init(&bars[kTpReady], 1); mbar_init(&bars[kTpReady + 1], 1);
+        mbar_init(&bars[kWFull], 1);
+        mbar_init(&bars[kKsideFull], 1); mbar_init(&bars[kKsideFull + 1], 1);
+        mbar_init(&bars[kKsideEmpty], 1); mbar_init(&bars[kKsideEmpty + 1], 1);
+        mbar_init(&bars[kD1Done], 1);
+        for (int hh = 0; hh < 2; ++hh) {
+            mbar_init(&bars[kSbReady + hh], 128); mbar_init(&bars[kVnFull + hh], 1);
+            mbar_init(&bars[kVnbReady + hh], 128); mbar_init(&bars[kSReady + hh], 1);
+            mbar_init(&bars[kOFull + hh], 1); mbar_init(&bars[kOFree + hh], 128);
+        }
         fence_mbar_init();
-        tma_prefetch_desc(&mq); tma_prefetch_desc(&mk); tma_prefetch_desc(&mv); tma_prefetch_desc(&mo);
     }
-    if (warp == 0) tmem_alloc(s_tmem, kTmemCols);
+    if (warp == 16) {
+        tmem_alloc(s_tmem, kTmemCols);
+        if (lane == 0) { tma_prefetch_desc(&mq); tma_prefetch_desc(&mk); tma_prefetch_desc(&mv); tma_prefetch_desc(&mo); }
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *s_tmem;
-    const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
-    const int vcol = wh * 128 + wq * 32 + lane;   // value column this thread owns on the state side
 
-    auto issue_loads = [&](int n, int st) {   // tid 0: TMA q,k,v tiles of chunk n into stage st
-        const int f = n / cpf, c0 = (n - f * cpf) << 6;
-        uint8_t* sp = smem + st * kStageBytes;
-        mbar_arrive_expect_tx(&bar_tma[st], stage_tx);
-        tma_load_5d(sp + kOffKt, &mk, &bar_tma[st], 0, c0, f, h, b);
-        tma_load_5d(sp + kOffQt, &mq, &bar_tma[st], 0, c0, f, h, b);
-        tma_load_5d(sp + kOffVt, &mv, &bar_tma[st], 0, c0, h * VB, f, b);
-    };
-    auto load_gates = [&](int n, float& gv, float& bv) {   // tid < 64: g, beta of row tid of chunk n
-        const int f = n / cpf, c = ((n - f * cpf) << 6) + tid;
-        gv = 0.f; bv = 0.f;                                  // pad rows: exact no-ops
-        if (c < C) {
-            const int64_t t = (int64_t)f * C + c;
-            gv = load_gate(p.g, g_off + t * p.g_stride[1], p.gate_dtype);
-            bv = load_gate(p.beta, bt_off + t * p.beta_stride[1], p.gate_dtype);
-        }
-    };
-
-    // ---- prologue: first tiles in flight, initial state into TMEM ----
-    if (tid == 0) issue_loads(0, 0);
-    if (tid < 64) { float gv, bv; load_gates(0, gv, bv); sG[tid] = gv; sBt[tid] = bv; }
-    if (state_warp) {
-        uint32_t r[32];
-        const float* s0 = p.initial_state ? p.initial_state + (int64_t)chain * 64 * V + vcol : nullptr;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = s0 ? __float_as_uint(__ldg(s0 + (int64_t)(half * 32 + j) * V)) : 0u;
-            tmem_st32(lane_addr + kColS + wh * 64 + half * 32, r);
-        }
-        tmem_wait_st();
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-
-    uint32_t mma_phase = 0;
     constexpr uint32_t kIdKK = umma_idesc_bf16(128, 64, false, false);
     constexpr uint32_t kIdMnA = umma_idesc_bf16(128, 64, true, false);          // A = tile^T (MN-major), B K-major
     constexpr uint32_t kIdMnB = umma_idesc_bf16(128, 64, false, true);          // TS, B MN-major
     constexpr uint32_t kIdMnBneg = umma_idesc_bf16(128, 64, false, true, true); // TS, -A, B MN-major
 
-    for (int n = 0; n < NC; ++n) {
-        const int st = n & 1;
-        uint8_t* sp = smem + st * kStageBytes;
-        const uint32_t aKt = sbase + st * kStageBytes + kOffKt, aQt = aKt + 8192, aVt = aKt + 16384;
-        const float* gS = sG + st * 64;
-        const float* btS = sBt + st * 64;
-        const int f = n / cpf, c0 = (n - f * cpf) << 6;
+    if (warp < 8) {
+        // =========================================================================================
+        // K-side group
+        // =========================================================================================
+        const int wq = warp & 3, wh = warp >> 2;
+        const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
+        const int64_t g_off = (int64_t)b * p.g_stride[0] + (int64_t)h * p.g_stride[2];
+        const int64_t bt_off = (int64_t)b * p.beta_stride[0] + (int64_t)h * p.beta_stride[2];
+        auto load_gates = [&](int n, float& gv, float& bv) {   // tid < 64: g, beta of row tid of chunk n
+            const int f = n / cpf, c = ((n - f * cpf) << 6) + tid;
+            gv = 0.f; bv = 0.f;                                  // pad rows: exact no-ops
+            if (c < C) {
+                const int64_t t = (int64_t)f * C + c;
+                gv = load_gate(p.g, g_off + t * p.g_stride[1], p.gate_dtype);
+                bv = load_gate(p.beta, bt_off + t * p.beta_stride[1], p.gate_dtype);
+            }
+        };
+        if (tid < 64) { float gv, bv; load_gates(0, gv, bv); sG[tid] = gv; sBt[tid] = bv; }
+        named_bar_sync(1, kKThreads);
 
-        // (0) prefetch chunk n+1 (its stage was released at the end of chunk n-1)
-        float g_next = 0.f, b_next = 0.f;
-        if (n + 1 < NC) {
-            if (tid == 0) issue_loads(n + 1, st ^ 1);
-            if (tid < 64) load_gates(n + 1, g_next, b_next);
-        }
+        for (int n = 0; n < NC; ++n) {
+            const int st = n & 1;
+            uint8_t* sp = smem + st * kStageBytes;
+            const float* gS = sG + st * 64;
+            const float* btS = sBt + st * 64;
+            float g_next = 0.f, b_next = 0.f;
+            if (n + 1 < NC && tid < 64) load_gates(n + 1, g_next, b_next);
+            // operand buffers (and gamma slot) of this stage are free once every MMA of chunk n-2 has completed
+            if (n >= 2) mbar_wait(&bars[kKsideEmpty + st], (uint32_t)((n >> 1) - 1) & 1u);
 
-        // (1) tiles of chunk n have landed
-        mbar_wait(&bar_tma[st], (uint32_t)(n >> 1) & 1u);
+            // gate scan (warp 0): Gamma = cumsum(g), decay factors, fast/slow decision
+            if (warp == 0) {
+                const float g0 = gS[2 * lane], g1 = gS[2 * lane + 1];
+                float s = g0 + g1;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const float t = __shfl_up_sync(0xffffffffu, s, off);
+                    if (lane >= off) s += t;
+                }
+                const float G1 = s, G0 = s - g1;
+                const float Gl = __shfl_sync(0xffffffffu, s, 31);
+                const bool fast = Gl > -60.f;
+                const float gam = __expf(Gl);
+                sGam[2 * lane] = G0; sGam[2 * lane + 1] = G1;
+                sE[2 * lane] = __expf(G0); sE[2 * lane + 1] = __expf(G1);
+                sCj[2 * lane] = btS[2 * lane] * (fast ? __expf(-G0) : 1.f);
+                sCj[2 * lane + 1] = btS[2 * lane + 1] * (fast ? __expf(-G1) : 1.f);
+                sKd[2 * lane] = fast ? gam : __expf(Gl - G0);
+                sKd[2 * lane + 1] = fast ? gam : __expf(Gl - G1);
+                if (lane == 0) { sGamma[st] = gam; sFast[0] = fast ? 1.f : 0.f; }
+            }
+            named_bar_sync(1, kKThreads);
+            const bool fast = sFast[0] != 0.f;
 
-        // (2) [K;Q] K^T  ->  TMEM KQ
-        if (tid == 0) {
+            // [K;Q]K^T accumulators -> A (fp32 solve matrix) and P (bf16 operand)
+            mbar_wait(&bars[kTmaFull + st], (uint32_t)(n >> 1) & 1u);   // tiles visible to this thread's loads
+            mbar_wait(&bars[kKqFull], (uint32_t)n & 1u);
             tc_fence_after_sync();
+            {
+                uint32_t r[32];
+                tmem_ld32(lane_addr + kColKQ + wh * 32, r);
+                tmem_wait_ld();
+                if (wq < 2) {          // rows of K K^T:  A_ij = beta_i (k_i.k_j) [* exp(Gamma_i - Gamma_j)],  j < i
+                    const int i = wq * 32 + lane;
+                    const float Gi = sGam[i], bi = btS[i];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = umma_smem_desc_sw128(aKt + k * 32, 16, 1024);
-                umma_ss(tmem + kColKQ, ad, ad, kIdKK, k > 0);
-            }
-            umma_commit(bar_mma);
-        }
-        // gate scan (warp 0): Gamma = cumsum(g) and the per-row decay factors
-        if (warp == 0) {
-            const float g0 = gS[2 * lane], g1 = gS[2 * lane + 1];
-            float s = g0 + g1;
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        float o[4];
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const float t = __shfl_up_sync(0xffffffffu, s, off);
-                if (lane >= off) s += t;
-            }
-            const float G1 = s, G0 = s - g1;
-            const float Gl = __shfl_sync(0xffffffffu, s, 31);
-            sGam[2 * lane] = G0; sGam[2 * lane + 1] = G1;
-            sE[2 * lane] = __expf(G0); sE[2 * lane + 1] = __expf(G1);
-            sFi[2 * lane] = __expf(-G0); sFi[2 * lane + 1] = __expf(-G1);
-            sKd[2 * lane] = __expf(Gl - G0); sKd[2 * lane + 1] = __expf(Gl - G1);
-            if (lane == 0) { sScal[0] = __expf(Gl); sScal[1] = Gl > -60.f ? 1.f : 0.f; }
-        }
-        __syncthreads();
-        const bool fast = sScal[1] != 0.f;
-
-        // (3) KQ -> gated A (fp32, solve matrix) and P (bf16 operand); row scalings of the tiles
-        mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
-        tc_fence_after_sync();
-        {
-            uint32_t r[32];
-            tmem_ld32(lane_addr + kColKQ + wh * 32, r);
-            tmem_wait_ld();
-            if (wq < 2) {          // rows of K K^T
-                const int i = wq * 32 + lane;
-                const float Gi = sGam[i], bi = btS[i], bie = bi * sE[i];
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    float o[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int j = wh * 32 + j4 * 4 + jj;
-                        const float w = fast ? bie * sFi[j] : bi * __expf(Gi - sGam[j]);
-                        o[jj] = j < i ? __uint_as_float(r[j4 * 4 + jj]) * w : 0.f;
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = wh * 32 + j4 * 4 + jj;
+                            const float w = fast ? bi : bi * __expf(Gi - sGam[j]);
+                            o[jj] = j < i ? __uint_as_float(r[j4 * 4 + jj]) * w : 0.f;
+                        }
+                        *reinterpret_cast<float4*>(sA + i * kPitchA + wh * 32 + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
                     }
-                    *reinterpret_cast<float4*>(sA + i * kPitchA + wh * 32 + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
-                }
-            } else {               // rows of Q K^T
-                const int i = (wq - 2) * 32 + lane;
-                const float Gi = sGam[i], sce = scale * sE[i];
+                } else {               // rows of Q K^T:  P_ij = scale e_i (q_i.k_j)  |  scale exp(Gamma_i - Gamma_j) (q_i.k_j),  j <= i
+                    const int i = (wq - 2) * 32 + lane;
+                    const float Gi = sGam[i], sce = scale * sE[i];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float o[8];
+                    for (int c = 0; c < 4; ++c) {
+                        float o[8];
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const int j = wh * 32 + c * 8 + jj;
-                        const float w = fast ? sce * sFi[j] : scale * __expf(Gi - sGam[j]);
-                        o[jj] = j <= i ? __uint_as_float(r[c * 8 + jj]) * w : 0.f;
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const int j = wh * 32 + c * 8 + jj;
+                            const float w = fast ? sce : scale * __expf(Gi - sGam[j]);
+                            o[jj] = j <= i ? __uint_as_float(r[c * 8 + jj]) * w : 0.f;
+                        }
+                        *reinterpret_cast<uint4*>(smem + kOffPp + st * 8192 + sw128_offset(i, wh * 4 + c)) =
+                            make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
                     }
-                    *reinterpret_cast<uint4*>(smem + kOffPp + sw128_offset(i, wh * 4 + c)) =
-                        make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
                 }
             }
-        }
-#pragma unroll
-        for (int idx = tid; idx < 512; idx += kThreads) {      // (row, 16B chunk): swizzle keeps rows intact
-            const int row = idx >> 3, off = idx << 4;
-            const float e = sE[row];
-            uint4* pk = reinterpret_cast<uint4*>(sp + kOffKt + off);
-            uint4* pq = reinterpret_cast<uint4*>(sp + kOffQt + off);
-            const uint4 kv = *pk;
-            *reinterpret_cast<uint4*>(smem + kOffKp + off) = scale_row8(kv, sKd[row]);   // K'
-            *pk = scale_row8(kv, e);                                                      // K~
-            *pq = scale_row8(*pq, scale * e);                                             // Q~
-        }
-        tc_fence_before_sync();
-        __syncthreads();
+            tc_fence_before_sync();
+            named_bar_sync(1, kKThreads);
 
-        // (4) T = (I + A)^-1 : 16x16 forward substitution, then two block-merge levels
-        if (tid < 64) {
-            const int blk = tid >> 4, c = tid & 15;
-            float* Ab = sA + (blk * 16) * kPitchA + blk * 16;
-            float x[16], acc[16];
+            // 16x16 diagonal blocks by forward substitution (warps 0-1) while warps 2-7 rescale the tiles
+            if (warp < 2) {
+                const int blk = tid >> 4, c = tid & 15;
+                float* Ab = sA + (blk * 16) * kPitchA + blk * 16;
+                float x[16], acc[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+                for (int i = 0; i < 16; ++i) acc[i] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                x[j] = (j == c) ? 1.f : -acc[j];
+                for (int j = 0; j < 16; ++j) {
+                    x[j] = (j == c) ? 1.f : -acc[j];
 #pragma unroll
-                for (int i = j + 1; i < 16; ++i) acc[i] = fmaf(Ab[i * kPitchA + j], x[j], acc[i]);
-            }
-            __syncwarp();
+                    for (int i = j + 1; i < 16; ++i) acc[i] = fmaf(Ab[i * kPitchA + j], x[j], acc[i]);
+                }
+                __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) Ab[i * kPitchA + c] = x[i];
-        }
-        __syncthreads();
-        tri_merge<16, 2>(sA, sY, tid);
-        tri_merge<32, 1>(sA, sY, tid);
-        {   // T' = T diag(beta) -> bf16, K-major swizzled rows
-            const int i = tid >> 2, cb = (tid & 3) * 2;
-#pragma unroll
-            for (int c = cb; c < cb + 2; ++c) {
-                const float4 x0 = *reinterpret_cast<const float4*>(sA + i * kPitchA + c * 8);
-                const float4 x1 = *reinterpret_cast<const float4*>(sA + i * kPitchA + c * 8 + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(btS + c * 8);
-                const float4 b1 = *reinterpret_cast<const float4*>(btS + c * 8 + 4);
-                *reinterpret_cast<uint4*>(smem + kOffTp + sw128_offset(i, c)) =
-                    make_uint4(pack_bf16(x0.x * b0.x, x0.y * b0.y), pack_bf16(x0.z * b0.z, x0.w * b0.w),
-                               pack_bf16(x1.x * b1.x, x1.y * b1.y), pack_bf16(x1.z * b1.z, x1.w * b1.w));
-            }
-        }
-        fence_proxy_async_smem();
-        __syncthreads();
-
-        // (5) W^T = K~^T T'^T -> TMEM KQ region ;  Vn^T[h] = V^T[h] T'^T
-        if (tid == 0) {
-            tc_fence_after_sync();
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint64_t bd = umma_smem_desc_sw128(sbase + kOffTp + k * 32, 16, 1024);
-                umma_ss(tmem + kColKQ, umma_smem_desc_sw128(aKt + k * 2048, 8192, 1024), bd, kIdMnA, k > 0);
-            }
-            for (int hh = 0; hh < NH; ++hh) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const uint64_t bd = umma_smem_desc_sw128(sbase + kOffTp + k * 32, 16, 1024);
-                    umma_ss(tmem + kColVn + hh * 64, umma_smem_desc_sw128(aVt + hh * 16384 + k * 2048, 8192, 1024), bd, kIdMnA, k > 0);
+                for (int i = 0; i < 16; ++i) Ab[i * kPitchA + c] = x[i];
+            } else {
+                for (int idx = tid - 64; idx < 512; idx += kKThreads - 64) {   // (row, 16B chunk): swizzle keeps rows intact
+                    const int row = idx >> 3, off = idx << 4;
+                    const float e = sE[row];
+                    uint4* pk = reinterpret_cast<uint4*>(sp + kOffKt + off);
+                    uint4* pq = reinterpret_cast<uint4*>(sp + kOffQt + off);
+                    const uint4 kv = *pk;
+                    *reinterpret_cast<uint4*>(smem + kOffKp + st * 8192 + off) = scale_row8(kv, sKd[row]);   // K'
+                    *pk = scale_row8(kv, e);                                                                  // K~
+                    *pq = scale_row8(*pq, scale * e);                                                         // Q~
                 }
             }
-            umma_commit(bar_mma);
-        }
-        //     meanwhile: Sb = bf16(S^T) (operand copy), S^T <- gamma S^T (decay before the accumulate)
-        if (state_warp) {
-            const float gam = sScal[0];
-            uint32_t r[32], pk[32];
+            named_bar_sync(1, kKThreads);
+            tri_merge<16, 2>(sA, sY, warp, lane);
+            tri_merge<32, 1>(sA, sY, warp, lane);
+            // T' = X diag(c) -> bf16, K-major swizzled rows (thread: 4 consecutive columns of one row, 4 tasks)
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld32(lane_addr + kColS + wh * 64 + half * 32, r);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) pk[half * 16 + j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-#pragma unroll
-                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * gam);
-                tmem_st32(lane_addr + kColS + wh * 64 + half * 32, r);
+            for (int it = 0; it < 4; ++it) {
+                const int task = it * kKThreads + tid, i = task >> 4, q4 = task & 15;
+                const float4 x = *reinterpret_cast<const float4*>(sA + i * kPitchA + q4 * 4);
+                const float4 cj = *reinterpret_cast<const float4*>(sCj + q4 * 4);
+                *reinterpret_cast<uint2*>(smem + kOffTp + st * 8192 + sw128_offset(i, q4 >> 1) + (q4 & 1) * 8) =
+                    make_uint2(pack_bf16(x.x * cj.x, x.y * cj.y), pack_bf16(x.z * cj.z, x.w * cj.w));
             }
-            tmem_st32(lane_addr + kColSb + wh * 32, pk);
-            tmem_wait_st();
-        }
-        tc_fence_before_sync();
+            fence_proxy_async_smem();
+            named_bar_sync(1, kKThreads);
+            if (tid == 0) mbar_arrive(&bars[kTpReady + st]);
 
-        // (6) W^T accumulators -> bf16 MN-major operand rows (row = key dim d, contiguous over tokens)
-        mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
-        tc_fence_after_sync();
-        if (wq < 2) {
-            uint32_t r[32];
-            const int d = wq * 32 + lane;
-            tmem_ld32(lane_addr + kColKQ + wh * 32, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-                *reinterpret_cast<uint4*>(smem + kOffWt + sw128_offset(d, wh * 4 + c)) =
-                    make_uint4(pack_bf16(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1])),
-                               pack_bf16(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3])),
-                               pack_bf16(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5])),
-                               pack_bf16(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7])));
-        }
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
-
-        // (7) Vn^T[h] -= Sb[h] W^T ;  O^T[h] = Sb[h] Q~^T
-        if (tid == 0) {
+            // W^T accumulators -> bf16 MN-major operand rows (row = key dim d, contiguous over tokens)
+            mbar_wait(&bars[kWFull], (uint32_t)n & 1u);
             tc_fence_after_sync();
-            for (int hh = 0; hh < NH; ++hh) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_ts(tmem + kColVn + hh * 64, tmem + kColSb + hh * 32 + k * 8,
-                            umma_smem_desc_sw128(sbase + kOffWt + k * 2048, 8192, 1024), kIdMnBneg, true);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_ts(tmem + kColO + hh * 64, tmem + kColSb + hh * 32 + k * 8,
-                            umma_smem_desc_sw128(aQt + k * 32, 16, 1024), kIdKK, k > 0);
-            }
-            umma_commit(bar_mma);
-            tma_store_wait_read0();     // previous chunk's readout has left the staging buffer
-        }
-
-        // (8) Vnb = bf16(Vn^T) written over the first half of Vn (TMEM A-operand)
-        mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
-        tc_fence_after_sync();
-        if (state_warp) {
-            uint32_t r[32], pk[32];
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld32(lane_addr + kColVn + wh * 64 + half * 32, r);
+            if (wq < 2) {
+                uint32_t r[32];
+                const int d = wq * 32 + lane;
+                tmem_ld32(lane_addr + kColKQ + wh * 32, r);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) pk[half * 16 + j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4*>(smem + kOffWt + st * 8192 + sw128_offset(d, wh * 4 + c)) =
+                        make_uint4(pack_bf16(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1])),
+                                   pack_bf16(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3])),
+                                   pack_bf16(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5])),
+                                   pack_bf16(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7])));
             }
-            tmem_st32(lane_addr + kColVn + wh * 64, pk);
-            tmem_wait_st();
+            if (n + 1 < NC && tid < 64) { sG[(st ^ 1) * 64 + tid] = g_next; sBt[(st ^ 1) * 64 + tid] = b_next; }
+            fence_proxy_async_smem();
+            tc_fence_before_sync();
+            named_bar_sync(1, kKThreads);
+            if (tid == 0) mbar_arrive(&bars[kKsideFull + st]);
         }
-        tc_fence_before_sync();
-        __syncthreads();
-
-        // (9) S^T[h] += Vnb[h] K' ;  O^T[h] += Vnb[h] P^T
-        if (tid == 0) {
+    } else if (warp < 16) {
+        // =========================================================================================
+        // state warpgroups (one per 128 value columns)
+        // =========================================================================================
+        const int hh = (warp - 8) >> 2, wq = warp & 3, stid = tid - 256 - hh * 128;
+        if (hh < NH) {
+            const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
+            const int vcol = hh * 128 + wq * 32 + lane;
+            const int bar_id = 2 + hh;
+            __nv_bfloat16* ost = reinterpret_cast<__nv_bfloat16*>(smem + kOffOst + hh * 16384) + (wq >> 1) * 4096 + ((wq & 1) * 32 + lane);
+            {   // initial state -> TMEM
+                uint32_t r[32];
+                const float* s0 = p.initial_state ? p.initial_state + (int64_t)chain * 64 * V + vcol : nullptr;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = s0 ? __float_as_uint(__ldg(s0 + (int64_t)(half * 32 + j) * V)) : 0u;
+                    tmem_st32(lane_addr + kColS + hh * 64 + half * 32, r);
+                }
+                tmem_wait_st();
+            }
+            // drain the readout of chunk m: O^T -> bf16 -> staging [2][tok][64] -> TMA store (rows past the frame are clipped)
+            auto readout = [&](int m) {
+                uint32_t r0[32], r1[32];
+                mbar_wait(&bars[kOFull + hh], (uint32_t)m & 1u);
+                tc_fence_after_sync();
+                tmem_ld32(lane_addr + kColO + hh * 64, r0);
+                tmem_ld32(lane_addr + kColO + hh * 64 + 32, r1);
+                tmem_wait_ld();
+                tc_fence_before_sync();
+                mbar_arrive(&bars[kOFree + hh]);
+                if (stid == 0) tma_store_wait_read0();      // previous readout has left the staging buffer
+                named_bar_sync(bar_id, 128);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ost[j * 64] = __float2bfloat16_rn(__uint_as_float(r0[j]));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) ost[(32 + j) * 64] = __float2bfloat16_rn(__uint_as_float(r1[j]));
+                fence_proxy_async_smem();
+                named_bar_sync(bar_id, 128);
+                if (stid == 0) {
+                    const int f = m / cpf, c0 = (m - f * cpf) << 6;
+                    tma_store_5d(&mo, smem + kOffOst + hh * 16384, 0, c0, h * VB + hh * 2, f, b);
+                    tma_store_commit();
+                }
+            };
+            for (int n = 0; n < NC; ++n) {
+                const int st = n & 1;
+                mbar_wait(&bars[kKsideFull + st], (uint32_t)(n >> 1) & 1u);       // gamma of chunk n published
+                if (n >= 1) mbar_wait(&bars[kSReady + hh], (uint32_t)(n - 1) & 1u);
+                tc_fence_after_sync();
+                {   // Sb = bf16(S^T) (operand copy), S^T <- gamma S^T (decay before the accumulate)
+                    const float gam = sGamma[st];
+                    uint32_t r[32], pk[32];
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        tmem_ld32(lane_addr + kColS + hh * 64 + half * 32, r);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[half * 16 + j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * gam);
+                        tmem_st32(lane_addr + kColS + hh * 64 + half * 32, r);
+                    }
+                    tmem_st32(lane_addr + kColSb + hh * 32, pk);
+                    tmem_wait_st();
+                }
+                tc_fence_before_sync();
+                mbar_arrive(&bars[kSbReady + hh]);
+                if (n >= 1) readout(n - 1);                                         // in the shadow of the Vn MMAs
+                mbar_wait(&bars[kVnFull + hh], (uint32_t)n & 1u);
+                tc_fence_after_sync();
+                {   // Vnb = bf16(Vn^T) written over the first half of Vn (TMEM A-operand)
+                    uint32_t r[32], pk[32];
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        tmem_ld32(lane_addr + kColVn + hh * 64 + half * 32, r);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[half * 16 + j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                    }
+                    tmem_st32(lane_addr + kColVn + hh * 64, pk);
+                    tmem_wait_st();
+                }
+                tc_fence_before_sync();
+                mbar_arrive(&bars[kVnbReady + hh]);
+            }
+            readout(NC - 1);
+            mbar_wait(&bars[kSReady + hh], (uint32_t)(NC - 1) & 1u);
             tc_fence_after_sync();
-            for (int hh = 0; hh < NH; ++hh) {
+            if (p.final_state != nullptr) {
+                uint32_t r[32];
+                float* sT = p.final_state + (int64_t)chain * 64 * V + vcol;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_ts(tmem + kColS + hh * 64, tmem + kColVn + hh * 64 + k * 8,
-                            umma_smem_desc_sw128(sbase + kOffKp + k * 2048, 8192, 1024), kIdMnB, true);
+                for (int half = 0; half < 2; ++half) {
+                    tmem_ld32(lane_addr + kColS + hh * 64 + half * 32, r);
+                    tmem_wait_ld();
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_ts(tmem + kColO + hh * 64, tmem + kColVn + hh * 64 + k * 8,
-                            umma_smem_desc_sw128(sbase + kOffPp + k * 32, 16, 1024), kIdKK, true);
+                    for (int j = 0; j < 32; ++j) sT[(int64_t)(half * 32 + j) * V] = __uint_as_float(r[j]);
+                }
             }
-            umma_commit(bar_mma);
+            if (stid == 0) tma_store_wait_all0();
+            tc_fence_before_sync();
         }
-
-        // (10) readout: O^T -> bf16 -> staging [V/64][tok][64] -> TMA store (rows past the frame are clipped)
-        mbar_wait(bar_mma, mma_phase); mma_phase ^= 1;
-        tc_fence_after_sync();
-        if (state_warp) {
-            uint32_t r[32];
-            __nv_bfloat16* ost = reinterpret_cast<__nv_bfloat16*>(smem + kOffOst) + (vcol >> 6) * 4096 + (vcol & 63);
+    } else if (warp == 16) {
+        // =========================================================================================
+        // issuer K: TMA loads + the two K-side MMAs
+        // =========================================================================================
+        if (lane == 0) {
+            const uint32_t stage_tx = 16384u + (uint32_t)VB * 8192u;
+            auto issue_loads = [&](int n) {
+                const int st = n & 1, f = n / cpf, c0 = (n - f * cpf) << 6;
+                uint8_t* sp = smem + st * kStageBytes;
+                mbar_arrive_expect_tx(&bars[kTmaFull + st], stage_tx);
+                tma_load_5d(sp + kOffKt, &mk, &bars[kTmaFull + st], 0, c0, f, h, b);
+                tma_load_5d(sp + kOffQt, &mq, &bars[kTmaFull + st], 0, c0, f, h, b);
+                tma_load_5d(sp + kOffVt, &mv, &bars[kTmaFull + st], 0, c0, h * VB, f, b);
+            };
+            issue_loads(0);
+            for (int n = 0; n < NC; ++n) {
+                const int st = n & 1;
+                const uint32_t aKt = sbase + st * kStageBytes + kOffKt;
+                mbar_wait(&bars[kTmaFull + st], (uint32_t)(n >> 1) & 1u);
+                if (n >= 1) mbar_wait(&bars[kKsideFull + (st ^ 1)], (uint32_t)((n - 1) >> 1) & 1u);   // KQ region drained
+                tc_fence_after_sync();
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                tmem_ld32(lane_addr + kColO + wh * 64 + half * 32, r);
-                tmem_wait_ld();
+                for (int k = 0; k < 4; ++k) {        // [K;Q] K^T
+                    const uint64_t ad = umma_smem_desc_sw128(aKt + k * 32, 16, 1024);
+                    umma_ss(tmem + kColKQ, ad, ad, kIdKK, k > 0);
+                }
+                umma_commit(&bars[kKqFull]);
+                if (n + 1 < NC) {                    // refill the other stage: chunk n-1 no longer reads it
+                    if (n >= 1) mbar_wait(&bars[kD1Done], (uint32_t)(n - 1) & 1u);
+                    issue_loads(n + 1);
+                }
+                mbar_wait(&bars[kTpReady + st], (uint32_t)(n >> 1) & 1u);
+                tc_fence_after_sync();
 #pragma unroll
-                for (int j = 0; j < 32; ++j) ost[(half * 32 + j) * 64] = __float2bfloat16_rn(__uint_as_float(r[j]));
+                for (int k = 0; k < 4; ++k)          // W^T = K~^T T'^T
+                    umma_ss(tmem + kColKQ, umma_smem_desc_sw128(aKt + k * 2048, 8192, 1024),
+                            umma_smem_desc_sw128(sbase + kOffTp + st * 8192 + k * 32, 16, 1024), kIdMnA, k > 0);
+                umma_commit(&bars[kWFull]);
             }
         }
-        if (n + 1 < NC && tid < 64) { sG[(st ^ 1) * 64 + tid] = g_next; sBt[(st ^ 1) * 64 + tid] = b_next; }
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tma_store_5d(&mo, smem + kOffOst, 0, c0, h * VB, f, b);
-            tma_store_commit();
+        __syncwarp();
+    } else {
+        // =========================================================================================
+        // issuer S: the state-side MMAs
+        // =========================================================================================
+        if (lane == 0) {
+            for (int n = 0; n < NC; ++n) {
+                const int st = n & 1;
+                const uint32_t aQt = sbase + st * kStageBytes + kOffQt, aVt = aQt + 8192;
+                const uint32_t aTp = sbase + kOffTp + st * 8192, aWt = sbase + kOffWt + st * 8192;
+                const uint32_t aKp = sbase + kOffKp + st * 8192, aPp = sbase + kOffPp + st * 8192;
+                mbar_wait(&bars[kTpReady + st], (uint32_t)(n >> 1) & 1u);
+                tc_fence_after_sync();
+                for (int hh = 0; hh < NH; ++hh)      // Vn^T[h] = V^T[h] T'^T   (in order after the MMAs of chunk n-1)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_ss(tmem + kColVn + hh * 64, umma_smem_desc_sw128(aVt + hh * 16384 + k * 2048, 8192, 1024),
+                                umma_smem_desc_sw128(aTp + k * 32, 16, 1024), kIdMnA, k > 0);
+                mbar_wait(&bars[kKsideFull + st], (uint32_t)(n >> 1) & 1u);
+                for (int hh = 0; hh < NH; ++hh) {    // Vn^T[h] -= Sb[h] W^T
+                    mbar_wait(&bars[kSbReady + hh], (uint32_t)n & 1u);
+                    tc_fence_after_sync();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_ts(tmem + kColVn + hh * 64, tmem + kColSb + hh * 32 + k * 8,
+                                umma_smem_desc_sw128(aWt + k * 2048, 8192, 1024), kIdMnBneg, true);
+                    umma_commit(&bars[kVnFull + hh]);
+                }
+                for (int hh = 0; hh < NH; ++hh) {    // O^T[h] = Sb[h] Q~^T
+                    if (n >= 1) mbar_wait(&bars[kOFree + hh], (uint32_t)(n - 1) & 1u);
+                    tc_fence_after_sync();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_ts(tmem + kColO + hh * 64, tmem + kColSb + hh * 32 + k * 8,
+                                umma_smem_desc_sw128(aQt + k * 32, 16, 1024), kIdKK, k > 0);
+                }
+                umma_commit(&bars[kD1Done]);
+                for (int hh = 0; hh < NH; ++hh) {    // S^T[h] += Vnb[h] K' ;  O^T[h] += Vnb[h] P^T
+                    mbar_wait(&bars[kVnbReady + hh], (uint32_t)n & 1u);
+                    tc_fence_after_sync();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_ts(tmem + kColS + hh * 64, tmem + kColVn + hh * 64 + k * 8,
+                                umma_smem_desc_sw128(aKp + k * 2048, 8192, 1024), kIdMnB, true);
+                    umma_commit(&bars[kSReady + hh]);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_ts(tmem + kColO + hh * 64, tmem + kColVn + hh * 64 + k * 8,
+                                umma_smem_desc_sw128(aPp + k * 32, 16, 1024), kIdKK, true);
+                    umma_commit(&bars[kOFull + hh]);
+                }
+                umma_commit(&bars[kKsideEmpty + st]);
+            }
         }
+        __syncwarp();
     }
 
-    // ---- epilogue: final state, drain the last store, release TMEM ----
-    tc_fence_after_sync();
-    if (state_warp && p.final_state != nullptr) {
-        uint32_t r[32];
-        float* sT = p.final_state + (int64_t)chain * 64 * V + vcol;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            tmem_ld32(lane_addr + kColS + wh * 64 + half * 32, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sT[(int64_t)(half * 32 + j) * V] = __uint_as_float(r[j]);
-        }
-    }
-    if (tid == 0) tma_store_wait_all0();
+    // ---- teardown ----
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+    if (warp == 16) tmem_dealloc(tmem, kTmemCols);
 }
 
 bool mult16(int64_t elems) { return (elems * 2) % 16 == 0; }
@@ -525,14 +627,16 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
         if (rc == 0) rc = make_tmap(&mk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.k, dims, sk, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc != 0) return (int)cudaErrorInvalidValue;
     }
-    // v,o: (64 values, token-in-frame, head x value-block, frame, clip)
+    // v: (64 values, token-in-frame, head x value-block, frame, clip), whole V per box;
+    // o: same geometry, one 128-column half per box (each state warpgroup stores its own half)
     {
         const uint64_t dims[5] = {64, (uint64_t)C, H * (V / 64), (uint64_t)F, B};
-        const uint32_t box[5] = {64, 64, (uint32_t)(V / 64), 1, 1};
+        const uint32_t boxv[5] = {64, 64, (uint32_t)(V / 64), 1, 1};
+        const uint32_t boxo[5] = {64, 64, 2, 1, 1};
         const uint64_t sv[4] = {(uint64_t)p.v_stride[1] * 2, 128, (uint64_t)p.v_stride[1] * 2 * C, (uint64_t)p.v_stride[0] * 2};
         const uint64_t so[4] = {(uint64_t)p.o_stride[1] * 2, 128, (uint64_t)p.o_stride[1] * 2 * C, (uint64_t)p.o_stride[0] * 2};
-        int rc = make_tmap(&mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.v, dims, sv, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc == 0) rc = make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.o, dims, so, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        int rc = make_tmap(&mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.v, dims, sv, boxv, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc == 0) rc = make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.o, dims, so, boxo, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc != 0) return (int)cudaErrorInvalidValue;
     }
     gdr_chunk_kernel<<<p.B * p.H, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, C, F);
