@@ -60,8 +60,8 @@ constexpr uint32_t kOffOst = kOffTp + 16384;     // readout staging, per value h
 constexpr uint32_t kOffA = kOffOst + 32768;      // fp32 solve matrix
 constexpr uint32_t kOffY = kOffA + 64 * kPitchA * 4;
 constexpr uint32_t kOffF = kOffY + 32 * kPitchY * 4;
-//   floats: g[2][64] beta[2][64] Gam[64] E[64] Cj[64] Kd[64] gamma[2] fast[1] pad[1]
-constexpr uint32_t kNumFloats = 8 * 64 + 4;
+//   floats: g[2][64] beta[2][64] Gam[2][64] E[2][64] Cj[2][64] Kd[2][64] gamma[4] fast[2] pad[2]
+constexpr uint32_t kNumFloats = 12 * 64 + 8;
 constexpr uint32_t kOffBar = kOffF + kNumFloats * 4;
 constexpr uint32_t kNumBars = 24;
 constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;   // + tmem slot + alignment slack
@@ -79,9 +79,9 @@ constexpr uint32_t kTmemCols = 512;
 enum Bar : int {
     kTmaFull = 0,    // [2] tiles of a chunk landed                      (tx)      -> issuer K, K group
     kKqFull = 2,     //     [K;Q]K^T accumulators complete                (commit)  -> K group
-    kTpReady = 3,    // [2] T' (and K~, Q~, K', P) written                (1)       -> issuer K (W), issuer S (U)
-    kWFull = 5,      //     W^T accumulators complete                     (commit)  -> K group
-    kKsideFull = 6,  // [2] W^T operand + gamma published (K side done)   (1)       -> issuer K/S, state groups
+    kKqFree = 3,     //     [K;Q]K^T accumulators drained                 (256)     -> issuer K
+    kTpReady = 4,    // [2] T' (and K~, Q~, K', P) written                (1)       -> issuer S (U)
+    kKsideFull = 6,  // [2] W^T operand + gamma published (K side done)   (1)       -> issuer S, state groups
     kKsideEmpty = 8, // [2] every MMA of the chunk completed              (commit)  -> K group (operand buffers free)
     kD1Done = 10,    //     tile stage no longer read by any MMA          (commit)  -> issuer K (TMA refill)
     kSbReady = 11,   // [2] per half: Sb + decayed S in TMEM              (128)     -> issuer S
@@ -95,6 +95,7 @@ enum Bar : int {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void kbar() { named_bar_sync(1, kKThreads); }
 
 __device__ __forceinline__ uint32_t scale_bf16x2(uint32_t w, float s) {
     const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
@@ -104,7 +105,7 @@ __device__ __forceinline__ uint4 scale_row8(uint4 v, float s) {
     return make_uint4(scale_bf16x2(v.x, s), scale_bf16x2(v.y, s), scale_bf16x2(v.z, s), scale_bf16x2(v.w, s));
 }
 
-// ---- 3xTF32 warp MMA: fp32-grade 16x8 += 16x8k * 8kx8 on the legacy tensor path (tiny, K-side only) ----
+// ---- warp-level MMA on the legacy tensor path: tiny K-side products that live in registers ----
 __device__ __forceinline__ uint32_t to_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -116,26 +117,52 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-// c(16x8) += A[0..15][kbeg..kend) * B[kbeg..kend)[0..7];  A row-major pitch pa, B row-major pitch pb
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// c(16x8) += A[0..15][kbeg..kend) * B[kbeg..kend)[0..7] in 3xTF32 (fp32-grade); A, B row-major fp32 in
+// shared memory with pitches pa, pb; kbeg/kend warp-uniform multiples of 8 within [0, 8*KS).
+// Three independent accumulators keep the tensor pipe chain at KS dependent MMAs instead of 3*KS.
+template <int KS>
 __device__ __forceinline__ void tile_mma_3xtf32(float (&c)[4], const float* A, int pa, const float* B, int pb,
                                                 int kbeg, int kend, int lane) {
     const int g = lane >> 2, t = lane & 3;
-    for (int k0 = kbeg; k0 < kend; k0 += 8) {
-        const float af[4] = {A[g * pa + k0 + t], A[(g + 8) * pa + k0 + t], A[g * pa + k0 + t + 4], A[(g + 8) * pa + k0 + t + 4]};
-        const float bf[2] = {B[(k0 + t) * pb + g], B[(k0 + t + 4) * pb + g]};
-        uint32_t ah[4], al[4], bh[2], bl[2];
+    float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { ah[i] = to_tf32(af[i]); al[i] = to_tf32(af[i] - __uint_as_float(ah[i])); }
+    for (int ks = 0; ks < KS; ++ks) {
+        const int k0 = ks * 8;
+        if (k0 >= kbeg && k0 < kend) {
+            const float af[4] = {A[g * pa + k0 + t], A[(g + 8) * pa + k0 + t], A[g * pa + k0 + t + 4], A[(g + 8) * pa + k0 + t + 4]};
+            const float bf[2] = {B[(k0 + t) * pb + g], B[(k0 + t + 4) * pb + g]};
+            uint32_t ah[4], al[4], bh[2], bl[2];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) { bh[i] = to_tf32(bf[i]); bl[i] = to_tf32(bf[i] - __uint_as_float(bh[i])); }
-        mma_tf32(c, al, bh);
-        mma_tf32(c, ah, bl);
-        mma_tf32(c, ah, bh);
+            for (int i = 0; i < 4; ++i) { ah[i] = to_tf32(af[i]); al[i] = to_tf32(af[i] - __uint_as_float(ah[i])); }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { bh[i] = to_tf32(bf[i]); bl[i] = to_tf32(bf[i] - __uint_as_float(bh[i])); }
+            mma_tf32(c, ah, bh);
+            mma_tf32(c1, al, bh);
+            mma_tf32(c2, ah, bl);
+        }
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] += c1[i] + c2[i];
 }
 
 // X21 <- -X22 (L21 X11) for NP independent pairs of adjacent N x N diagonal blocks of the unit
-// lower-triangular matrix held in sA (in place; sY is scratch).  Called by the whole K group.
+// lower-triangular matrix held in sA (in place; sY is scratch).  Called by the whole K group;
+// `idle_work` runs on the last warp between the two stages' barriers (it has no tile when NP*tiles < 8).
 template <int N, int NP>
 __device__ __forceinline__ void tri_merge(float* sA, float* sY, int warp, int lane) {
     constexpr int NT = N / 8, TPP = (N / 16) * NT, TILES = NP * TPP;
@@ -145,19 +172,52 @@ __device__ __forceinline__ void tri_merge(float* sA, float* sY, int warp, int la
     float* Y = sY + pair * (N * kPitchY);
     if (warp < TILES) {      // Y = L21 X11   (X11 lower triangular: rows k < 8 nt contribute nothing)
         float c[4] = {0.f, 0.f, 0.f, 0.f};
-        tile_mma_3xtf32(c, sA + (o2 + mt * 16) * kPitchA + o1, kPitchA, sA + o1 * kPitchA + o1 + nt * 8, kPitchA, nt * 8, N, lane);
+        tile_mma_3xtf32<N / 8>(c, sA + (o2 + mt * 16) * kPitchA + o1, kPitchA, sA + o1 * kPitchA + o1 + nt * 8, kPitchA, nt * 8, N, lane);
         *reinterpret_cast<float2*>(Y + (mt * 16 + g) * kPitchY + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
         *reinterpret_cast<float2*>(Y + (mt * 16 + g + 8) * kPitchY + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
     }
-    named_bar_sync(1, kKThreads);
+    kbar();
     if (warp < TILES) {      // X21 = -X22 Y  (X22 lower triangular: columns k > row contribute nothing)
         float c[4] = {0.f, 0.f, 0.f, 0.f};
-        tile_mma_3xtf32(c, sA + (o2 + mt * 16) * kPitchA + o2, kPitchA, Y + nt * 8, kPitchY, 0, mt * 16 + 16, lane);
+        tile_mma_3xtf32<N / 8>(c, sA + (o2 + mt * 16) * kPitchA + o2, kPitchA, Y + nt * 8, kPitchY, 0, mt * 16 + 16, lane);
         float* X21 = sA + (o2 + mt * 16) * kPitchA + o1 + nt * 8 + 2 * t;
         *reinterpret_cast<float2*>(X21 + g * kPitchA) = make_float2(-c[0], -c[1]);
         *reinterpret_cast<float2*>(X21 + (g + 8) * kPitchA) = make_float2(-c[2], -c[3]);
     }
-    named_bar_sync(1, kKThreads);
+    kbar();
+}
+
+// Gate scan of one chunk (one warp): Gamma = cumsum(g), decay factors, fast/slow decision.
+__device__ __forceinline__ void gate_scan(const float* gS, const float* btS, float* sGam, float* sE, float* sCj,
+                                          float* sKd, float* sFast, float* gamma_slot, int lane) {
+    const float g0 = gS[2 * lane], g1 = gS[2 * lane + 1];
+    float s = g0 + g1;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, s, off);
+        if (lane >= off) s += t;
+    }
+    const float G1 = s, G0 = s - g1;
+    const float Gl = __shfl_sync(0xffffffffu, s, 31);
+    const bool fast = Gl > -60.f;
+    const float gam = __expf(Gl);
+    sGam[2 * lane] = G0; sGam[2 * lane + 1] = G1;
+    sE[2 * lane] = __expf(G0); sE[2 * lane + 1] = __expf(G1);
+    sCj[2 * lane] = btS[2 * lane] * (fast ? __expf(-G0) : 1.f);          // column factor of T'
+    sCj[2 * lane + 1] = btS[2 * lane + 1] * (fast ? __expf(-G1) : 1.f);
+    sKd[2 * lane] = fast ? gam : __expf(Gl - G0);                         // row factor of K'
+    sKd[2 * lane + 1] = fast ? gam : __expf(Gl - G1);
+    if (lane == 0) { *gamma_slot = gam; *sFast = fast ? 1.f : 0.f; }
+}
+
+// four 128x64x16 tcgen05 MMAs covering K = 64; descriptors advance by a fixed step per K slice
+__device__ __forceinline__ void umma4_ss(uint32_t d, uint64_t a, uint32_t astep, uint64_t bdesc, uint32_t bstep, uint32_t idesc, bool acc0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_ss(d, a + (uint64_t)(k * astep), bdesc + (uint64_t)(k * bstep), idesc, acc0 || k > 0);
+}
+__device__ __forceinline__ void umma4_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t bstep, uint32_t idesc, bool acc0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) umma_ts(d, a_tmem + k * 8, bdesc + (uint64_t)(k * bstep), idesc, acc0 || k > 0);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -173,12 +233,12 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     float* sY = reinterpret_cast<float*>(smem + kOffY);
     float* sG = reinterpret_cast<float*>(smem + kOffF);   // [2][64] log gates of the chunk in each stage
     float* sBt = sG + 128;                                // [2][64] beta
-    float* sGam = sBt + 128;                              // Gamma_i (inclusive cumsum of g)
-    float* sE = sGam + 64;                                // exp(Gamma_i)
-    float* sCj = sE + 64;                                 // column factor of T': f_j beta_j (fast) | beta_j (slow)
-    float* sKd = sCj + 64;                                // row factor of K':    gamma (fast) | exp(Gamma_last - Gamma_i) (slow)
-    float* sGamma = sKd + 64;                             // [2] exp(Gamma_last) of the chunk in each stage
-    float* sFast = sGamma + 2;
+    float* sGam = sBt + 128;                              // [2][64] Gamma_i (inclusive cumsum of g)
+    float* sE = sGam + 128;                               // [2][64] exp(Gamma_i)
+    float* sCj = sE + 128;                                // [2][64] column factor of T': f_j beta_j (fast) | beta_j (slow)
+    float* sKd = sCj + 128;                               // [2][64] row factor of K':    gamma (fast) | exp(Gamma_last - Gamma_i) (slow)
+    float* sGamma = sKd + 128;                            // [4] exp(Gamma_last) of chunk n in slot n & 3
+    float* sFast = sGamma + 4;                            // [2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
@@ -190,9 +250,8 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
 
     if (tid == 0) {
         mbar_init(&bars[kTmaFull], 1); mbar_init(&bars[kTmaFull + 1], 1);
-        mbar_init(&bars[kKqFull], 1);
+        mbar_init(&bars[kKqFull], 1); mbar_init(&bars[kKqFree], kKThreads);
         mbar_init(&bars[kTpReady], 1); mbar_init(&bars[kTpReady + 1], 1);
-        mbar_init(&bars[kWFull], 1);
         mbar_init(&bars[kKsideFull], 1); mbar_init(&bars[kKsideFull + 1], 1);
         mbar_init(&bars[kKsideEmpty], 1); mbar_init(&bars[kKsideEmpty + 1], 1);
         mbar_init(&bars[kD1Done], 1);
@@ -235,43 +294,22 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             }
         };
         if (tid < 64) { float gv, bv; load_gates(0, gv, bv); sG[tid] = gv; sBt[tid] = bv; }
-        named_bar_sync(1, kKThreads);
+        kbar();
+        if (warp == 7) gate_scan(sG, sBt, sGam, sE, sCj, sKd, sFast, sGamma, lane);
+        kbar();
 
         for (int n = 0; n < NC; ++n) {
             const int st = n & 1;
             uint8_t* sp = smem + st * kStageBytes;
-            const float* gS = sG + st * 64;
             const float* btS = sBt + st * 64;
+            const float* eS = sE + st * 64;
             float g_next = 0.f, b_next = 0.f;
             if (n + 1 < NC && tid < 64) load_gates(n + 1, g_next, b_next);
-            // operand buffers (and gamma slot) of this stage are free once every MMA of chunk n-2 has completed
+            // operand buffers of this stage are free once every MMA of chunk n-2 has completed
             if (n >= 2) mbar_wait(&bars[kKsideEmpty + st], (uint32_t)((n >> 1) - 1) & 1u);
+            const bool fast = sFast[st] != 0.f;
 
-            // gate scan (warp 0): Gamma = cumsum(g), decay factors, fast/slow decision
-            if (warp == 0) {
-                const float g0 = gS[2 * lane], g1 = gS[2 * lane + 1];
-                float s = g0 + g1;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const float t = __shfl_up_sync(0xffffffffu, s, off);
-                    if (lane >= off) s += t;
-                }
-                const float G1 = s, G0 = s - g1;
-                const float Gl = __shfl_sync(0xffffffffu, s, 31);
-                const bool fast = Gl > -60.f;
-                const float gam = __expf(Gl);
-                sGam[2 * lane] = G0; sGam[2 * lane + 1] = G1;
-                sE[2 * lane] = __expf(G0); sE[2 * lane + 1] = __expf(G1);
-                sCj[2 * lane] = btS[2 * lane] * (fast ? __expf(-G0) : 1.f);
-                sCj[2 * lane + 1] = btS[2 * lane + 1] * (fast ? __expf(-G1) : 1.f);
-                sKd[2 * lane] = fast ? gam : __expf(Gl - G0);
-                sKd[2 * lane + 1] = fast ? gam : __expf(Gl - G1);
-                if (lane == 0) { sGamma[st] = gam; sFast[0] = fast ? 1.f : 0.f; }
-            }
-            named_bar_sync(1, kKThreads);
-            const bool fast = sFast[0] != 0.f;
-
-            // [K;Q]K^T accumulators -> A (fp32 solve matrix) and P (bf16 operand)
+            // [K;Q]K^T accumulators -> masked A (fp32 solve matrix) and P (bf16 operand), row factors only
             mbar_wait(&bars[kTmaFull + st], (uint32_t)(n >> 1) & 1u);   // tiles visible to this thread's loads
             mbar_wait(&bars[kKqFull], (uint32_t)n & 1u);
             tc_fence_after_sync();
@@ -279,39 +317,51 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 uint32_t r[32];
                 tmem_ld32(lane_addr + kColKQ + wh * 32, r);
                 tmem_wait_ld();
-                if (wq < 2) {          // rows of K K^T:  A_ij = beta_i (k_i.k_j) [* exp(Gamma_i - Gamma_j)],  j < i
+                tc_fence_before_sync();
+                mbar_arrive(&bars[kKqFree]);
+                if (wq < 2) {          // rows of K K^T:  A_ij = beta_i (k_i.k_j),  j < i
                     const int i = wq * 32 + lane;
-                    const float Gi = sGam[i], bi = btS[i];
+                    const float bi = btS[i];
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         float o[4];
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const int j = wh * 32 + j4 * 4 + jj;
-                            const float w = fast ? bi : bi * __expf(Gi - sGam[j]);
-                            o[jj] = j < i ? __uint_as_float(r[j4 * 4 + jj]) * w : 0.f;
-                        }
+                        for (int jj = 0; jj < 4; ++jj)
+                            o[jj] = (wh * 32 + j4 * 4 + jj) < i ? __uint_as_float(r[j4 * 4 + jj]) * bi : 0.f;
                         *reinterpret_cast<float4*>(sA + i * kPitchA + wh * 32 + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
                     }
-                } else {               // rows of Q K^T:  P_ij = scale e_i (q_i.k_j)  |  scale exp(Gamma_i - Gamma_j) (q_i.k_j),  j <= i
+                } else {               // rows of Q K^T:  P_ij = scale e_i (q_i.k_j),  j <= i
                     const int i = (wq - 2) * 32 + lane;
-                    const float Gi = sGam[i], sce = scale * sE[i];
+                    const float sce = fast ? scale * eS[i] : scale;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float o[8];
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            const int j = wh * 32 + c * 8 + jj;
-                            const float w = fast ? sce : scale * __expf(Gi - sGam[j]);
-                            o[jj] = j <= i ? __uint_as_float(r[c * 8 + jj]) * w : 0.f;
-                        }
+                        for (int jj = 0; jj < 8; ++jj)
+                            o[jj] = (wh * 32 + c * 8 + jj) <= i ? __uint_as_float(r[c * 8 + jj]) * sce : 0.f;
                         *reinterpret_cast<uint4*>(smem + kOffPp + st * 8192 + sw128_offset(i, wh * 4 + c)) =
                             make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
                     }
                 }
             }
-            tc_fence_before_sync();
-            named_bar_sync(1, kKThreads);
+            kbar();
+            if (!fast) {   // rare: chunk decay below e^-60 -> per-element exp(Gamma_i - Gamma_j) instead of folded factors
+                const float* Gm = sGam + st * 64;
+#pragma unroll 1
+                for (int idx = tid; idx < 4096; idx += kKThreads) {
+                    const int i = idx >> 6, j = idx & 63;
+                    if (j < i) sA[i * kPitchA + j] *= __expf(Gm[i] - Gm[j]);
+                }
+#pragma unroll 1
+                for (int idx = tid; idx < 2048; idx += kKThreads) {
+                    const int i = idx >> 5, j = (idx & 31) * 2;
+                    uint32_t* w = reinterpret_cast<uint32_t*>(smem + kOffPp + st * 8192 + sw128_offset(i, j >> 3) + (j & 7) * 2);
+                    const uint32_t v = *w;
+                    *w = pack_bf16(__uint_as_float(v << 16) * __expf(fminf(Gm[i] - Gm[j], 0.f)),
+                                   __uint_as_float(v & 0xffff0000u) * __expf(fminf(Gm[i] - Gm[j + 1], 0.f)));
+                }
+                kbar();
+            }
 
             // 16x16 diagonal blocks by forward substitution (warps 0-1) while warps 2-7 rescale the tiles
             if (warp < 2) {
@@ -329,54 +379,76 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 __syncwarp();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) Ab[i * kPitchA + c] = x[i];
+                if (n + 1 < NC) { sG[(st ^ 1) * 64 + tid] = g_next; sBt[(st ^ 1) * 64 + tid] = b_next; }
             } else {
+                const float* kdS = sKd + st * 64;
+#pragma unroll 1
                 for (int idx = tid - 64; idx < 512; idx += kKThreads - 64) {   // (row, 16B chunk): swizzle keeps rows intact
                     const int row = idx >> 3, off = idx << 4;
-                    const float e = sE[row];
+                    const float e = eS[row];
                     uint4* pk = reinterpret_cast<uint4*>(sp + kOffKt + off);
                     uint4* pq = reinterpret_cast<uint4*>(sp + kOffQt + off);
                     const uint4 kv = *pk;
-                    *reinterpret_cast<uint4*>(smem + kOffKp + st * 8192 + off) = scale_row8(kv, sKd[row]);   // K'
+                    *reinterpret_cast<uint4*>(smem + kOffKp + st * 8192 + off) = scale_row8(kv, kdS[row]);   // K'
                     *pk = scale_row8(kv, e);                                                                  // K~
                     *pq = scale_row8(*pq, scale * e);                                                         // Q~
                 }
             }
-            named_bar_sync(1, kKThreads);
+            kbar();
+            // block merges; warp 7 has no 16x16 merge tile and scans the gates of chunk n+1 meanwhile
+            if (warp == 7 && n + 1 < NC)
+                gate_scan(sG + (st ^ 1) * 64, sBt + (st ^ 1) * 64, sGam + (st ^ 1) * 64, sE + (st ^ 1) * 64, sCj + (st ^ 1) * 64,
+                          sKd + (st ^ 1) * 64, sFast + (st ^ 1), sGamma + ((n + 1) & 3), lane);
             tri_merge<16, 2>(sA, sY, warp, lane);
             tri_merge<32, 1>(sA, sY, warp, lane);
-            // T' = X diag(c) -> bf16, K-major swizzled rows (thread: 4 consecutive columns of one row, 4 tasks)
+            {   // T' = X diag(c) -> bf16, K-major swizzled rows (thread: 4 consecutive columns of one row, 4 tasks)
+                const float* cjS = sCj + st * 64;
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {
-                const int task = it * kKThreads + tid, i = task >> 4, q4 = task & 15;
-                const float4 x = *reinterpret_cast<const float4*>(sA + i * kPitchA + q4 * 4);
-                const float4 cj = *reinterpret_cast<const float4*>(sCj + q4 * 4);
-                *reinterpret_cast<uint2*>(smem + kOffTp + st * 8192 + sw128_offset(i, q4 >> 1) + (q4 & 1) * 8) =
-                    make_uint2(pack_bf16(x.x * cj.x, x.y * cj.y), pack_bf16(x.z * cj.z, x.w * cj.w));
+                for (int it = 0; it < 4; ++it) {
+                    const int task = it * kKThreads + tid, i = task >> 4, q4 = task & 15;
+                    const float4 x = *reinterpret_cast<const float4*>(sA + i * kPitchA + q4 * 4);
+                    const float4 cj = *reinterpret_cast<const float4*>(cjS + q4 * 4);
+                    *reinterpret_cast<uint2*>(smem + kOffTp + st * 8192 + sw128_offset(i, q4 >> 1) + (q4 & 1) * 8) =
+                        make_uint2(pack_bf16(x.x * cj.x, x.y * cj.y), pack_bf16(x.z * cj.z, x.w * cj.w));
+                }
             }
             fence_proxy_async_smem();
-            named_bar_sync(1, kKThreads);
+            kbar();
             if (tid == 0) mbar_arrive(&bars[kTpReady + st]);
 
-            // W^T accumulators -> bf16 MN-major operand rows (row = key dim d, contiguous over tokens)
-            mbar_wait(&bars[kWFull], (uint32_t)n & 1u);
-            tc_fence_after_sync();
-            if (wq < 2) {
-                uint32_t r[32];
-                const int d = wq * 32 + lane;
-                tmem_ld32(lane_addr + kColKQ + wh * 32, r);
-                tmem_wait_ld();
+            // W^T[d][i] = sum_j K~[j][d] T'[i][j] in registers (bf16 mma.sync, ldmatrix from the swizzled tiles)
+            // -> bf16 MN-major operand rows (row = key dim d, contiguous over tokens i)
+            {
+                const int mt = warp & 3, ng = warp >> 2, g = lane >> 2, t = lane & 3;
+                const uint32_t aK = sbase + st * kStageBytes + kOffKt, aT = sbase + kOffTp + st * 8192;
+                float acc[4][4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<uint4*>(smem + kOffWt + st * 8192 + sw128_offset(d, wh * 4 + c)) =
-                        make_uint4(pack_bf16(__uint_as_float(r[c * 8 + 0]), __uint_as_float(r[c * 8 + 1])),
-                                   pack_bf16(__uint_as_float(r[c * 8 + 2]), __uint_as_float(r[c * 8 + 3])),
-                                   pack_bf16(__uint_as_float(r[c * 8 + 4]), __uint_as_float(r[c * 8 + 5])),
-                                   pack_bf16(__uint_as_float(r[c * 8 + 6]), __uint_as_float(r[c * 8 + 7])));
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    if (ks * 16 <= ng * 32 + 31) {          // T' is lower triangular: j <= i
+                        uint32_t af[4], bf0[4], bf1[4];
+                        ldmatrix_x4_trans(af, aK + sw128_offset(ks * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, mt * 2 + ((lane >> 3) & 1)));
+                        ldmatrix_x4(bf0, aT + sw128_offset(ng * 32 + ((lane >> 4) & 1) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
+                        ldmatrix_x4(bf1, aT + sw128_offset(ng * 32 + 16 + ((lane >> 4) & 1) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
+                        mma_bf16(acc[0], af, bf0[0], bf0[1]);
+                        mma_bf16(acc[1], af, bf0[2], bf0[3]);
+                        mma_bf16(acc[2], af, bf1[0], bf1[1]);
+                        mma_bf16(acc[3], af, bf1[2], bf1[3]);
+                    }
+                }
+                uint8_t* wt = smem + kOffWt + st * 8192;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int i0 = ng * 32 + nt * 8 + 2 * t;
+                    *reinterpret_cast<uint32_t*>(wt + sw128_offset(mt * 16 + g, i0 >> 3) + (i0 & 7) * 2) = pack_bf16(acc[nt][0], acc[nt][1]);
+                    *reinterpret_cast<uint32_t*>(wt + sw128_offset(mt * 16 + g + 8, i0 >> 3) + (i0 & 7) * 2) = pack_bf16(acc[nt][2], acc[nt][3]);
+                }
             }
-            if (n + 1 < NC && tid < 64) { sG[(st ^ 1) * 64 + tid] = g_next; sBt[(st ^ 1) * 64 + tid] = b_next; }
             fence_proxy_async_smem();
-            tc_fence_before_sync();
-            named_bar_sync(1, kKThreads);
+            kbar();
             if (tid == 0) mbar_arrive(&bars[kKsideFull + st]);
         }
     } else if (warp < 16) {
@@ -430,7 +502,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 if (n >= 1) mbar_wait(&bars[kSReady + hh], (uint32_t)(n - 1) & 1u);
                 tc_fence_after_sync();
                 {   // Sb = bf16(S^T) (operand copy), S^T <- gamma S^T (decay before the accumulate)
-                    const float gam = sGamma[st];
+                    const float gam = sGamma[n & 3];
                     uint32_t r[32], pk[32];
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
@@ -484,7 +556,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         }
     } else if (warp == 16) {
         // =========================================================================================
-        // issuer K: TMA loads + the two K-side MMAs
+        // issuer K: TMA loads (one chunk of prefetch) + the [K;Q]K^T MMA
         // =========================================================================================
         if (lane == 0) {
             const uint32_t stage_tx = 16384u + (uint32_t)VB * 8192u;
@@ -497,29 +569,19 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 tma_load_5d(sp + kOffVt, &mv, &bars[kTmaFull + st], 0, c0, h * VB, f, b);
             };
             issue_loads(0);
+#pragma unroll 1
             for (int n = 0; n < NC; ++n) {
                 const int st = n & 1;
-                const uint32_t aKt = sbase + st * kStageBytes + kOffKt;
+                const uint64_t dK = umma_smem_desc_sw128(sbase + st * kStageBytes + kOffKt, 16, 1024);
                 mbar_wait(&bars[kTmaFull + st], (uint32_t)(n >> 1) & 1u);
-                if (n >= 1) mbar_wait(&bars[kKsideFull + (st ^ 1)], (uint32_t)((n - 1) >> 1) & 1u);   // KQ region drained
+                if (n >= 1) mbar_wait(&bars[kKqFree], (uint32_t)(n - 1) & 1u);      // accumulators of chunk n-1 drained
                 tc_fence_after_sync();
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {        // [K;Q] K^T
-                    const uint64_t ad = umma_smem_desc_sw128(aKt + k * 32, 16, 1024);
-                    umma_ss(tmem + kColKQ, ad, ad, kIdKK, k > 0);
-                }
+                umma4_ss(tmem + kColKQ, dK, 2, dK, 2, kIdKK, false);                // [K;Q] K^T
                 umma_commit(&bars[kKqFull]);
                 if (n + 1 < NC) {                    // refill the other stage: chunk n-1 no longer reads it
                     if (n >= 1) mbar_wait(&bars[kD1Done], (uint32_t)(n - 1) & 1u);
                     issue_loads(n + 1);
                 }
-                mbar_wait(&bars[kTpReady + st], (uint32_t)(n >> 1) & 1u);
-                tc_fence_after_sync();
-#pragma unroll
-                for (int k = 0; k < 4; ++k)          // W^T = K~^T T'^T
-                    umma_ss(tmem + kColKQ, umma_smem_desc_sw128(aKt + k * 2048, 8192, 1024),
-                            umma_smem_desc_sw128(sbase + kOffTp + st * 8192 + k * 32, 16, 1024), kIdMnA, k > 0);
-                umma_commit(&bars[kWFull]);
             }
         }
         __syncwarp();
@@ -528,49 +590,38 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         // issuer S: the state-side MMAs
         // =========================================================================================
         if (lane == 0) {
+#pragma unroll 1
             for (int n = 0; n < NC; ++n) {
                 const int st = n & 1;
                 const uint32_t aQt = sbase + st * kStageBytes + kOffQt, aVt = aQt + 8192;
-                const uint32_t aTp = sbase + kOffTp + st * 8192, aWt = sbase + kOffWt + st * 8192;
-                const uint32_t aKp = sbase + kOffKp + st * 8192, aPp = sbase + kOffPp + st * 8192;
+                const uint64_t dTp = umma_smem_desc_sw128(sbase + kOffTp + st * 8192, 16, 1024);
+                const uint64_t dWt = umma_smem_desc_sw128(sbase + kOffWt + st * 8192, 8192, 1024);
+                const uint64_t dKp = umma_smem_desc_sw128(sbase + kOffKp + st * 8192, 8192, 1024);
+                const uint64_t dPp = umma_smem_desc_sw128(sbase + kOffPp + st * 8192, 16, 1024);
+                const uint64_t dQt = umma_smem_desc_sw128(aQt, 16, 1024);
                 mbar_wait(&bars[kTpReady + st], (uint32_t)(n >> 1) & 1u);
                 tc_fence_after_sync();
                 for (int hh = 0; hh < NH; ++hh)      // Vn^T[h] = V^T[h] T'^T   (in order after the MMAs of chunk n-1)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_ss(tmem + kColVn + hh * 64, umma_smem_desc_sw128(aVt + hh * 16384 + k * 2048, 8192, 1024),
-                                umma_smem_desc_sw128(aTp + k * 32, 16, 1024), kIdMnA, k > 0);
+                    umma4_ss(tmem + kColVn + hh * 64, umma_smem_desc_sw128(aVt + hh * 16384, 8192, 1024), 128, dTp, 2, kIdMnA, false);
                 mbar_wait(&bars[kKsideFull + st], (uint32_t)(n >> 1) & 1u);
                 for (int hh = 0; hh < NH; ++hh) {    // Vn^T[h] -= Sb[h] W^T
                     mbar_wait(&bars[kSbReady + hh], (uint32_t)n & 1u);
                     tc_fence_after_sync();
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_ts(tmem + kColVn + hh * 64, tmem + kColSb + hh * 32 + k * 8,
-                                umma_smem_desc_sw128(aWt + k * 2048, 8192, 1024), kIdMnBneg, true);
+                    umma4_ts(tmem + kColVn + hh * 64, tmem + kColSb + hh * 32, dWt, 128, kIdMnBneg, true);
                     umma_commit(&bars[kVnFull + hh]);
                 }
                 for (int hh = 0; hh < NH; ++hh) {    // O^T[h] = Sb[h] Q~^T
                     if (n >= 1) mbar_wait(&bars[kOFree + hh], (uint32_t)(n - 1) & 1u);
                     tc_fence_after_sync();
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_ts(tmem + kColO + hh * 64, tmem + kColSb + hh * 32 + k * 8,
-                                umma_smem_desc_sw128(aQt + k * 32, 16, 1024), kIdKK, k > 0);
+                    umma4_ts(tmem + kColO + hh * 64, tmem + kColSb + hh * 32, dQt, 2, kIdKK, false);
                 }
                 umma_commit(&bars[kD1Done]);
                 for (int hh = 0; hh < NH; ++hh) {    // S^T[h] += Vnb[h] K' ;  O^T[h] += Vnb[h] P^T
                     mbar_wait(&bars[kVnbReady + hh], (uint32_t)n & 1u);
                     tc_fence_after_sync();
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_ts(tmem + kColS + hh * 64, tmem + kColVn + hh * 64 + k * 8,
-                                umma_smem_desc_sw128(aKp + k * 2048, 8192, 1024), kIdMnB, true);
+                    umma4_ts(tmem + kColS + hh * 64, tmem + kColVn + hh * 64, dKp, 128, kIdMnB, true);
                     umma_commit(&bars[kSReady + hh]);
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_ts(tmem + kColO + hh * 64, tmem + kColVn + hh * 64 + k * 8,
-                                umma_smem_desc_sw128(aPp + k * 32, 16, 1024), kIdKK, true);
+                    umma4_ts(tmem + kColO + hh * 64, tmem + kColVn + hh * 64, dPp, 2, kIdKK, true);
                     umma_commit(&bars[kOFull + hh]);
                 }
                 umma_commit(&bars[kKsideEmpty + st]);
