@@ -27,9 +27,13 @@
 // "f-folded" gating (fast path, chunk decay > e^-60): with e_i = exp(Gamma_i), f_j = exp(-Gamma_j)
 //     T = diag(e) X diag(f),  X = (I + strict_tril(beta_i k_i.k_j))^-1   (no decay inside the solve)
 // and the chunk is carried in the scaled variable V^_j = f_j Vnew_j, which turns every decay factor
-// into a row / column scaling:  T' = X diag(f beta), P = scale e_i (q_i.k_j)[j<=i], K' = gamma K.
-// Chunks with stronger decay use the per-element exp(Gamma_i - Gamma_j) form (slow path); both
-// produce the same five operands, so the MMA sequence is identical.
+// into a row / column / scalar factor that is applied where the data already passes through registers:
+//     T' = X diag(f beta)                      (column factor in the fp32 -> bf16 conversion of X)
+//     W  = T' (K e)                            (e_j applied to the K fragments of the in-register mma.sync)
+//     O  = diag(scale e) (Q S + tril(Q K^T) V^) (row factor applied in the readout epilogue; raw Q, unscaled P)
+//     S' = gamma (S + K^T V^)                  (raw K, loaded twice by TMA; gamma applied by the next S pass)
+// so the fast path never rescales a tile in shared memory.  Chunks with stronger decay use the
+// per-element exp(Gamma_i - Gamma_j) form (slow path, rare): same MMA sequence, tiles rescaled in place.
 //
 // Layout facts used here were verified on hardware by tests/probes/umma_probe.cu.
 // Math: oracle/gdr_ref.py::gdr_chunk_ref.
@@ -60,10 +64,10 @@ constexpr uint32_t kOffOst = kOffTp + 16384;     // readout staging, per value h
 constexpr uint32_t kOffA = kOffOst + 32768;      // fp32 solve matrix
 constexpr uint32_t kOffY = kOffA + 64 * kPitchA * 4;
 constexpr uint32_t kOffF = kOffY + 32 * kPitchY * 4;
-//   floats: g[2][64] beta[2][64] Gam[2][64] E[2][64] Cj[2][64] Kd[2][64] gamma[4] fast[2] pad[2]
-constexpr uint32_t kNumFloats = 12 * 64 + 8;
+//   floats: g[2][64] beta[2][64] Gam[2][64] E[2][64] Cj[2][64] Kd[2][64] Ofac[4][64] post[4] pre[4] fast[2] pad[2]
+constexpr uint32_t kNumFloats = 16 * 64 + 12;
 constexpr uint32_t kOffBar = kOffF + kNumFloats * 4;
-constexpr uint32_t kNumBars = 24;
+constexpr uint32_t kNumBars = 26;
 constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;   // + tmem slot + alignment slack
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
@@ -90,6 +94,7 @@ enum Bar : int {
     kSReady = 17,    // [2] per half: state update complete               (commit)  -> state group
     kOFull = 19,     // [2] per half: readout accumulators complete       (commit)  -> state group
     kOFree = 21,     // [2] per half: readout accumulators drained        (128)     -> issuer S
+    kKpFull = 23,    // [2] second copy of the K tile landed               (tx)      -> issuer S (state update), K group (slow path)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -106,11 +111,9 @@ __device__ __forceinline__ uint4 scale_row8(uint4 v, float s) {
 }
 
 // ---- warp-level MMA on the legacy tensor path: tiny K-side products that live in registers ----
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// tf32 "hi" part by truncation (the tensor core ignores the 13 low mantissa bits anyway); the exact
+// fp32 remainder x - hi is the "lo" part, so hi*hi + lo*hi + hi*lo carries ~21 mantissa bits.
+__device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x) & 0xffffe000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
     asm volatile(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -189,7 +192,8 @@ __device__ __forceinline__ void tri_merge(float* sA, float* sY, int warp, int la
 
 // Gate scan of one chunk (one warp): Gamma = cumsum(g), decay factors, fast/slow decision.
 __device__ __forceinline__ void gate_scan(const float* gS, const float* btS, float* sGam, float* sE, float* sCj,
-                                          float* sKd, float* sFast, float* gamma_slot, int lane) {
+                                          float* sKd, float* sFast, float* ofac, float* post, float* pre,
+                                          float scale, int lane) {
     const float g0 = gS[2 * lane], g1 = gS[2 * lane + 1];
     float s = g0 + g1;
 #pragma unroll
@@ -200,14 +204,16 @@ __device__ __forceinline__ void gate_scan(const float* gS, const float* btS, flo
     const float G1 = s, G0 = s - g1;
     const float Gl = __shfl_sync(0xffffffffu, s, 31);
     const bool fast = Gl > -60.f;
-    const float gam = __expf(Gl);
+    const float gam = __expf(Gl), e0 = __expf(G0), e1 = __expf(G1);
     sGam[2 * lane] = G0; sGam[2 * lane + 1] = G1;
-    sE[2 * lane] = __expf(G0); sE[2 * lane + 1] = __expf(G1);
+    sE[2 * lane] = e0; sE[2 * lane + 1] = e1;
     sCj[2 * lane] = btS[2 * lane] * (fast ? __expf(-G0) : 1.f);          // column factor of T'
     sCj[2 * lane + 1] = btS[2 * lane + 1] * (fast ? __expf(-G1) : 1.f);
-    sKd[2 * lane] = fast ? gam : __expf(Gl - G0);                         // row factor of K'
-    sKd[2 * lane + 1] = fast ? gam : __expf(Gl - G1);
-    if (lane == 0) { *gamma_slot = gam; *sFast = fast ? 1.f : 0.f; }
+    sKd[2 * lane] = __expf(Gl - G0);                                      // slow path: row factor of K'
+    sKd[2 * lane + 1] = __expf(Gl - G1);
+    ofac[2 * lane] = fast ? scale * e0 : 1.f;                             // readout row factor
+    ofac[2 * lane + 1] = fast ? scale * e1 : 1.f;
+    if (lane == 0) { *post = fast ? gam : 1.f; *pre = fast ? 1.f : gam; *sFast = fast ? 1.f : 0.f; }
 }
 
 // four 128x64x16 tcgen05 MMAs covering K = 64; descriptors advance by a fixed step per K slice
@@ -237,8 +243,10 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     float* sE = sGam + 128;                               // [2][64] exp(Gamma_i)
     float* sCj = sE + 128;                                // [2][64] column factor of T': f_j beta_j (fast) | beta_j (slow)
     float* sKd = sCj + 128;                               // [2][64] row factor of K':    gamma (fast) | exp(Gamma_last - Gamma_i) (slow)
-    float* sGamma = sKd + 128;                            // [4] exp(Gamma_last) of chunk n in slot n & 3
-    float* sFast = sGamma + 4;                            // [2]
+    float* sOfac = sKd + 128;                             // [4][64] readout row factor of chunk n in slot n & 3: scale e_i | 1
+    float* sPost = sOfac + 256;                           // [4] factor applied to S AFTER chunk n's accumulate: gamma | 1
+    float* sPre = sPost + 4;                              // [4] factor applied to S BEFORE chunk n's accumulate: 1 | gamma
+    float* sFast = sPre + 4;                              // [2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
@@ -255,6 +263,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         mbar_init(&bars[kKsideFull], 1); mbar_init(&bars[kKsideFull + 1], 1);
         mbar_init(&bars[kKsideEmpty], 1); mbar_init(&bars[kKsideEmpty + 1], 1);
         mbar_init(&bars[kD1Done], 1);
+        mbar_init(&bars[kKpFull], 1); mbar_init(&bars[kKpFull + 1], 1);
         for (int hh = 0; hh < 2; ++hh) {
             mbar_init(&bars[kSbReady + hh], 128); mbar_init(&bars[kVnFull + hh], 1);
             mbar_init(&bars[kVnbReady + hh], 128); mbar_init(&bars[kSReady + hh], 1);
@@ -295,7 +304,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         };
         if (tid < 64) { float gv, bv; load_gates(0, gv, bv); sG[tid] = gv; sBt[tid] = bv; }
         kbar();
-        if (warp == 7) gate_scan(sG, sBt, sGam, sE, sCj, sKd, sFast, sGamma, lane);
+        if (warp == 7) gate_scan(sG, sBt, sGam, sE, sCj, sKd, sFast, sOfac, sPost, sPre, scale, lane);
         kbar();
 
         for (int n = 0; n < NC; ++n) {
@@ -330,9 +339,9 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                             o[jj] = (wh * 32 + j4 * 4 + jj) < i ? __uint_as_float(r[j4 * 4 + jj]) * bi : 0.f;
                         *reinterpret_cast<float4*>(sA + i * kPitchA + wh * 32 + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
                     }
-                } else {               // rows of Q K^T:  P_ij = scale e_i (q_i.k_j),  j <= i
+                } else {               // rows of Q K^T:  P_ij = (q_i.k_j),  j <= i   (scale e_i is applied in the readout)
                     const int i = (wq - 2) * 32 + lane;
-                    const float sce = fast ? scale * eS[i] : scale;
+                    const float sce = fast ? 1.f : scale;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         float o[8];
@@ -360,10 +369,20 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                     *w = pack_bf16(__uint_as_float(v << 16) * __expf(fminf(Gm[i] - Gm[j], 0.f)),
                                    __uint_as_float(v & 0xffff0000u) * __expf(fminf(Gm[i] - Gm[j + 1], 0.f)));
                 }
+                mbar_wait(&bars[kKpFull + st], (uint32_t)(n >> 1) & 1u);
+                const float* kdS = sKd + st * 64;
+#pragma unroll 1
+                for (int idx = tid; idx < 512; idx += kKThreads) {   // (row, 16B chunk): the swizzle keeps rows intact
+                    const int row = idx >> 3, off = idx << 4;
+                    uint4* pk = reinterpret_cast<uint4*>(smem + kOffKp + st * 8192 + off);
+                    uint4* pq = reinterpret_cast<uint4*>(sp + kOffQt + off);
+                    *pk = scale_row8(*pk, kdS[row]);                 // K' = K exp(Gamma_last - Gamma_i)
+                    *pq = scale_row8(*pq, scale * eS[row]);          // Q~ = scale e_i Q
+                }
                 kbar();
             }
 
-            // 16x16 diagonal blocks by forward substitution (warps 0-1) while warps 2-7 rescale the tiles
+            // 16x16 diagonal blocks by forward substitution (warps 0-1)
             if (warp < 2) {
                 const int blk = tid >> 4, c = tid & 15;
                 float* Ab = sA + (blk * 16) * kPitchA + blk * 16;
@@ -380,25 +399,13 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < 16; ++i) Ab[i * kPitchA + c] = x[i];
                 if (n + 1 < NC) { sG[(st ^ 1) * 64 + tid] = g_next; sBt[(st ^ 1) * 64 + tid] = b_next; }
-            } else {
-                const float* kdS = sKd + st * 64;
-#pragma unroll 1
-                for (int idx = tid - 64; idx < 512; idx += kKThreads - 64) {   // (row, 16B chunk): swizzle keeps rows intact
-                    const int row = idx >> 3, off = idx << 4;
-                    const float e = eS[row];
-                    uint4* pk = reinterpret_cast<uint4*>(sp + kOffKt + off);
-                    uint4* pq = reinterpret_cast<uint4*>(sp + kOffQt + off);
-                    const uint4 kv = *pk;
-                    *reinterpret_cast<uint4*>(smem + kOffKp + st * 8192 + off) = scale_row8(kv, kdS[row]);   // K'
-                    *pk = scale_row8(kv, e);                                                                  // K~
-                    *pq = scale_row8(*pq, scale * e);                                                         // Q~
-                }
             }
             kbar();
             // block merges; warp 7 has no 16x16 merge tile and scans the gates of chunk n+1 meanwhile
             if (warp == 7 && n + 1 < NC)
                 gate_scan(sG + (st ^ 1) * 64, sBt + (st ^ 1) * 64, sGam + (st ^ 1) * 64, sE + (st ^ 1) * 64, sCj + (st ^ 1) * 64,
-                          sKd + (st ^ 1) * 64, sFast + (st ^ 1), sGamma + ((n + 1) & 3), lane);
+                          sKd + (st ^ 1) * 64, sFast + (st ^ 1), sOfac + ((n + 1) & 3) * 64, sPost + ((n + 1) & 3), sPre + ((n + 1) & 3),
+                          scale, lane);
             tri_merge<16, 2>(sA, sY, warp, lane);
             tri_merge<32, 1>(sA, sY, warp, lane);
             {   // T' = X diag(c) -> bf16, K-major swizzled rows (thread: 4 consecutive columns of one row, 4 tasks)
@@ -431,6 +438,14 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                     if (ks * 16 <= ng * 32 + 31) {          // T' is lower triangular: j <= i
                         uint32_t af[4], bf0[4], bf1[4];
                         ldmatrix_x4_trans(af, aK + sw128_offset(ks * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, mt * 2 + ((lane >> 3) & 1)));
+                        {   // K~ = K e_j: fragment registers hold tokens j = 16 ks + 2t (+1) and + 8
+                            const float2 e01 = *reinterpret_cast<const float2*>(eS + ks * 16 + 2 * t);
+                            const float2 e89 = *reinterpret_cast<const float2*>(eS + ks * 16 + 2 * t + 8);
+                            af[0] = pack_bf16(__uint_as_float(af[0] << 16) * e01.x, __uint_as_float(af[0] & 0xffff0000u) * e01.y);
+                            af[1] = pack_bf16(__uint_as_float(af[1] << 16) * e01.x, __uint_as_float(af[1] & 0xffff0000u) * e01.y);
+                            af[2] = pack_bf16(__uint_as_float(af[2] << 16) * e89.x, __uint_as_float(af[2] & 0xffff0000u) * e89.y);
+                            af[3] = pack_bf16(__uint_as_float(af[3] << 16) * e89.x, __uint_as_float(af[3] & 0xffff0000u) * e89.y);
+                        }
                         ldmatrix_x4(bf0, aT + sw128_offset(ng * 32 + ((lane >> 4) & 1) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
                         ldmatrix_x4(bf1, aT + sw128_offset(ng * 32 + 16 + ((lane >> 4) & 1) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
                         mma_bf16(acc[0], af, bf0[0], bf0[1]);
@@ -484,10 +499,23 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 mbar_arrive(&bars[kOFree + hh]);
                 if (stid == 0) tma_store_wait_read0();      // previous readout has left the staging buffer
                 named_bar_sync(bar_id, 128);
+                const float4* of4 = reinterpret_cast<const float4*>(sOfac + (m & 3) * 64);   // row factor scale e_i (or 1)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) ost[j * 64] = __float2bfloat16_rn(__uint_as_float(r0[j]));
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 c = of4[j4];
+                    ost[(j4 * 4 + 0) * 64] = __float2bfloat16_rn(__uint_as_float(r0[j4 * 4 + 0]) * c.x);
+                    ost[(j4 * 4 + 1) * 64] = __float2bfloat16_rn(__uint_as_float(r0[j4 * 4 + 1]) * c.y);
+                    ost[(j4 * 4 + 2) * 64] = __float2bfloat16_rn(__uint_as_float(r0[j4 * 4 + 2]) * c.z);
+                    ost[(j4 * 4 + 3) * 64] = __float2bfloat16_rn(__uint_as_float(r0[j4 * 4 + 3]) * c.w);
+                }
 #pragma unroll
-                for (int j = 0; j < 32; ++j) ost[(32 + j) * 64] = __float2bfloat16_rn(__uint_as_float(r1[j]));
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 c = of4[8 + j4];
+                    ost[(32 + j4 * 4 + 0) * 64] = __float2bfloat16_rn(__uint_as_float(r1[j4 * 4 + 0]) * c.x);
+                    ost[(32 + j4 * 4 + 1) * 64] = __float2bfloat16_rn(__uint_as_float(r1[j4 * 4 + 1]) * c.y);
+                    ost[(32 + j4 * 4 + 2) * 64] = __float2bfloat16_rn(__uint_as_float(r1[j4 * 4 + 2]) * c.z);
+                    ost[(32 + j4 * 4 + 3) * 64] = __float2bfloat16_rn(__uint_as_float(r1[j4 * 4 + 3]) * c.w);
+                }
                 fence_proxy_async_smem();
                 named_bar_sync(bar_id, 128);
                 if (stid == 0) {
@@ -501,17 +529,19 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 mbar_wait(&bars[kKsideFull + st], (uint32_t)(n >> 1) & 1u);       // gamma of chunk n published
                 if (n >= 1) mbar_wait(&bars[kSReady + hh], (uint32_t)(n - 1) & 1u);
                 tc_fence_after_sync();
-                {   // Sb = bf16(S^T) (operand copy), S^T <- gamma S^T (decay before the accumulate)
-                    const float gam = sGamma[n & 3];
+                {   // S_n = post_{n-1} * accumulator;  Sb = bf16(S_n) (operand copy);  accumulator <- pre_n * S_n
+                    const float post = n >= 1 ? sPost[(n - 1) & 3] : 1.f, pre = sPre[n & 3];
                     uint32_t r[32], pk[32];
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
                         tmem_ld32(lane_addr + kColS + hh * 64 + half * 32, r);
                         tmem_wait_ld();
 #pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * post);
+#pragma unroll
                         for (int j = 0; j < 16; ++j) pk[half * 16 + j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * gam);
+                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * pre);
                         tmem_st32(lane_addr + kColS + hh * 64 + half * 32, r);
                     }
                     tmem_st32(lane_addr + kColSb + hh * 32, pk);
@@ -542,13 +572,14 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             tc_fence_after_sync();
             if (p.final_state != nullptr) {
                 uint32_t r[32];
+                const float post = sPost[(NC - 1) & 3];
                 float* sT = p.final_state + (int64_t)chain * 64 * V + vcol;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     tmem_ld32(lane_addr + kColS + hh * 64 + half * 32, r);
                     tmem_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sT[(int64_t)(half * 32 + j) * V] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; ++j) sT[(int64_t)(half * 32 + j) * V] = __uint_as_float(r[j]) * post;
                 }
             }
             if (stid == 0) tma_store_wait_all0();
@@ -581,6 +612,12 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 if (n + 1 < NC) {                    // refill the other stage: chunk n-1 no longer reads it
                     if (n >= 1) mbar_wait(&bars[kD1Done], (uint32_t)(n - 1) & 1u);
                     issue_loads(n + 1);
+                }
+                {   // second copy of the K tile for the state update (raw K; its buffer is free once chunk n-2 completed)
+                    if (n >= 2) mbar_wait(&bars[kKsideEmpty + st], (uint32_t)((n >> 1) - 1) & 1u);
+                    const int f = n / cpf, c0 = (n - f * cpf) << 6;
+                    mbar_arrive_expect_tx(&bars[kKpFull + st], 8192u);
+                    tma_load_5d(smem + kOffKp + st * 8192, &mk, &bars[kKpFull + st], 0, c0, f, h, b);
                 }
             }
         }
@@ -616,6 +653,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                     umma4_ts(tmem + kColO + hh * 64, tmem + kColSb + hh * 32, dQt, 2, kIdKK, false);
                 }
                 umma_commit(&bars[kD1Done]);
+                mbar_wait(&bars[kKpFull + st], (uint32_t)(n >> 1) & 1u);
                 for (int hh = 0; hh < NH; ++hh) {    // S^T[h] += Vnb[h] K' ;  O^T[h] += Vnb[h] P^T
                     mbar_wait(&bars[kVnbReady + hh], (uint32_t)n & 1u);
                     tc_fence_after_sync();
