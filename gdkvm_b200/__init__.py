@@ -6,6 +6,6 @@ host-side mirror of the reference memory module's call surface.
 """
 from .ops import chunk_gated_delta_rule, gdr_lkva, gdr_lkva_out, launch_count, plan  # noqa: F401
 from .memory import GDRMemory  # noqa: F401
-from ._cabi import FLAG_FLAT_CHUNKS, FLAG_FORCE_CHUNKED, FLAG_FORCE_RECURRENT  # noqa: F401
+from ._cabi import FLAG_FLAT_CHUNKS, FLAG_FORCE_CHUNKED, FLAG_FORCE_RECURRENT, FLAG_FRAME_CHUNKS  # noqa: F401
 
 __version__ = "0.1.0"

@@ -10,7 +10,7 @@ from ._build import LIB_PATH
 
 GDKVM_ABI_VERSION = 1
 GDKVM_F32, GDKVM_BF16 = 0, 1
-FLAG_FORCE_RECURRENT, FLAG_FORCE_CHUNKED, FLAG_FLAT_CHUNKS = 0x1, 0x2, 0x4
+FLAG_FORCE_RECURRENT, FLAG_FORCE_CHUNKED, FLAG_FLAT_CHUNKS, FLAG_FRAME_CHUNKS = 0x1, 0x2, 0x4, 0x8
 
 EXPORTED_SYMBOLS = (
     "gdkvm_abi_version", "gdkvm_strerror", "gdkvm_last_cuda_error",

@@ -101,6 +101,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void kbar() { named_bar_sync(1, kKThreads); }
+// second K-group barrier (id 4) for the middle of the 16x16 merge, where warp 7 only arrives: a warp must
+// never arrive twice in one phase of the same barrier, so this cannot share id 1 with the full syncs
+__device__ __forceinline__ void kbar_mid() { named_bar_sync(4, kKThreads); }
+__device__ __forceinline__ void kbar_mid_arrive() { asm volatile("bar.arrive 4, %0;" ::"r"(kKThreads) : "memory"); }
 
 __device__ __forceinline__ uint32_t scale_bf16x2(uint32_t w, float s) {
     const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
@@ -111,14 +115,16 @@ __device__ __forceinline__ uint4 scale_row8(uint4 v, float s) {
 }
 
 // ---- warp-level MMA on the legacy tensor path: tiny K-side products that live in registers ----
-// tf32 "hi" part by truncation (the tensor core ignores the 13 low mantissa bits anyway); the exact
-// fp32 remainder x - hi is the "lo" part, so hi*hi + lo*hi + hi*lo carries ~21 mantissa bits.
-__device__ __forceinline__ uint32_t to_tf32(float x) { return __float_as_uint(x) & 0xffffe000u; }
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void mma_f16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
@@ -135,38 +141,34 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
-// c(16x8) += A[0..15][kbeg..kend) * B[kbeg..kend)[0..7] in 3xTF32 (fp32-grade); A, B row-major fp32 in
-// shared memory with pitches pa, pb; kbeg/kend warp-uniform multiples of 8 within [0, 8*KS).
-// Three independent accumulators keep the tensor pipe chain at KS dependent MMAs instead of 3*KS.
+// c(16x8) += A[0..15][k] * B[k][0..7] over the 16-wide k slices that intersect [kbeg, kend); A, B are
+// row-major fp32 in shared memory (pitches pa, pb), rounded to fp16 on the fly (11 significant bits;
+// every entry is O(1) and the result is rounded to bf16 afterwards -- tests/chunk_numerics_model.py).
+// Entries outside the triangular supports are exact zeros in memory, so partial slices are harmless.
 template <int KS>
-__device__ __forceinline__ void tile_mma_3xtf32(float (&c)[4], const float* A, int pa, const float* B, int pb,
-                                                int kbeg, int kend, int lane) {
+__device__ __forceinline__ void tile_mma_f16(float (&c)[4], const float* A, int pa, const float* B, int pb,
+                                             int kbeg, int kend, int lane) {
     const int g = lane >> 2, t = lane & 3;
-    float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
-        const int k0 = ks * 8;
-        if (k0 >= kbeg && k0 < kend) {
-            const float af[4] = {A[g * pa + k0 + t], A[(g + 8) * pa + k0 + t], A[g * pa + k0 + t + 4], A[(g + 8) * pa + k0 + t + 4]};
-            const float bf[2] = {B[(k0 + t) * pb + g], B[(k0 + t + 4) * pb + g]};
-            uint32_t ah[4], al[4], bh[2], bl[2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { ah[i] = to_tf32(af[i]); al[i] = to_tf32(af[i] - __uint_as_float(ah[i])); }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) { bh[i] = to_tf32(bf[i]); bl[i] = to_tf32(bf[i] - __uint_as_float(bh[i])); }
-            mma_tf32(c, ah, bh);
-            mma_tf32(c1, al, bh);
-            mma_tf32(c2, ah, bl);
+        const int k0 = ks * 16;
+        if (k0 + 16 > kbeg && k0 < kend) {
+            const float2 a0 = *reinterpret_cast<const float2*>(A + g * pa + k0 + 2 * t);
+            const float2 a1 = *reinterpret_cast<const float2*>(A + (g + 8) * pa + k0 + 2 * t);
+            const float2 a2 = *reinterpret_cast<const float2*>(A + g * pa + k0 + 2 * t + 8);
+            const float2 a3 = *reinterpret_cast<const float2*>(A + (g + 8) * pa + k0 + 2 * t + 8);
+            const uint32_t af[4] = {pack_f16(a0.x, a0.y), pack_f16(a1.x, a1.y), pack_f16(a2.x, a2.y), pack_f16(a3.x, a3.y)};
+            const float* Bk = B + (k0 + 2 * t) * pb + g;
+            mma_f16(c, af, pack_f16(Bk[0], Bk[pb]), pack_f16(Bk[8 * pb], Bk[9 * pb]));
         }
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) c[i] += c1[i] + c2[i];
 }
 
 // X21 <- -X22 (L21 X11) for NP independent pairs of adjacent N x N diagonal blocks of the unit
-// lower-triangular matrix held in sA (in place; sY is scratch).  Called by the whole K group;
-// `idle_work` runs on the last warp between the two stages' barriers (it has no tile when NP*tiles < 8).
-template <int N, int NP>
+// lower-triangular matrix held in sA (in place; sY is scratch).  Called by the whole K group.
+// With LAZY7, warp 7 (which has no tile) only arrives at the middle barrier: it runs the gate scan of
+// the next chunk across both stages.
+template <int N, int NP, bool LAZY7>
 __device__ __forceinline__ void tri_merge(float* sA, float* sY, int warp, int lane) {
     constexpr int NT = N / 8, TPP = (N / 16) * NT, TILES = NP * TPP;
     const int g = lane >> 2, t = lane & 3;
@@ -175,14 +177,14 @@ __device__ __forceinline__ void tri_merge(float* sA, float* sY, int warp, int la
     float* Y = sY + pair * (N * kPitchY);
     if (warp < TILES) {      // Y = L21 X11   (X11 lower triangular: rows k < 8 nt contribute nothing)
         float c[4] = {0.f, 0.f, 0.f, 0.f};
-        tile_mma_3xtf32<N / 8>(c, sA + (o2 + mt * 16) * kPitchA + o1, kPitchA, sA + o1 * kPitchA + o1 + nt * 8, kPitchA, nt * 8, N, lane);
+        tile_mma_f16<N / 16>(c, sA + (o2 + mt * 16) * kPitchA + o1, kPitchA, sA + o1 * kPitchA + o1 + nt * 8, kPitchA, nt * 8, N, lane);
         *reinterpret_cast<float2*>(Y + (mt * 16 + g) * kPitchY + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
         *reinterpret_cast<float2*>(Y + (mt * 16 + g + 8) * kPitchY + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
     }
-    kbar();
+    if (LAZY7) { if (warp != 7) kbar_mid(); } else kbar();
     if (warp < TILES) {      // X21 = -X22 Y  (X22 lower triangular: columns k > row contribute nothing)
         float c[4] = {0.f, 0.f, 0.f, 0.f};
-        tile_mma_3xtf32<N / 8>(c, sA + (o2 + mt * 16) * kPitchA + o2, kPitchA, Y + nt * 8, kPitchY, 0, mt * 16 + 16, lane);
+        tile_mma_f16<N / 16>(c, sA + (o2 + mt * 16) * kPitchA + o2, kPitchA, Y + nt * 8, kPitchY, 0, mt * 16 + 16, lane);
         float* X21 = sA + (o2 + mt * 16) * kPitchA + o1 + nt * 8 + 2 * t;
         *reinterpret_cast<float2*>(X21 + g * kPitchA) = make_float2(-c[0], -c[1]);
         *reinterpret_cast<float2*>(X21 + (g + 8) * kPitchA) = make_float2(-c[2], -c[3]);
@@ -322,37 +324,32 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             mbar_wait(&bars[kTmaFull + st], (uint32_t)(n >> 1) & 1u);   // tiles visible to this thread's loads
             mbar_wait(&bars[kKqFull], (uint32_t)n & 1u);
             tc_fence_after_sync();
-            {
-                uint32_t r[32];
-                tmem_ld32(lane_addr + kColKQ + wh * 32, r);
+#pragma unroll 1
+            for (int c8 = 0; c8 < 4; ++c8) {      // 8 accumulator columns per step keeps the loop body in the L0 i-cache
+                uint32_t r[8];
+                tmem_ld8(lane_addr + kColKQ + wh * 32 + c8 * 8, r);
                 tmem_wait_ld();
-                tc_fence_before_sync();
-                mbar_arrive(&bars[kKqFree]);
+                const int j0 = wh * 32 + c8 * 8;
                 if (wq < 2) {          // rows of K K^T:  A_ij = beta_i (k_i.k_j),  j < i
                     const int i = wq * 32 + lane;
                     const float bi = btS[i];
+                    float o[8];
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        float o[4];
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-                            o[jj] = (wh * 32 + j4 * 4 + jj) < i ? __uint_as_float(r[j4 * 4 + jj]) * bi : 0.f;
-                        *reinterpret_cast<float4*>(sA + i * kPitchA + wh * 32 + j4 * 4) = make_float4(o[0], o[1], o[2], o[3]);
-                    }
+                    for (int jj = 0; jj < 8; ++jj) o[jj] = (j0 + jj) < i ? __uint_as_float(r[jj]) * bi : 0.f;
+                    *reinterpret_cast<float4*>(sA + i * kPitchA + j0) = make_float4(o[0], o[1], o[2], o[3]);
+                    *reinterpret_cast<float4*>(sA + i * kPitchA + j0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
                 } else {               // rows of Q K^T:  P_ij = (q_i.k_j),  j <= i   (scale e_i is applied in the readout)
                     const int i = (wq - 2) * 32 + lane;
                     const float sce = fast ? 1.f : scale;
+                    float o[8];
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float o[8];
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj)
-                            o[jj] = (wh * 32 + c * 8 + jj) <= i ? __uint_as_float(r[c * 8 + jj]) * sce : 0.f;
-                        *reinterpret_cast<uint4*>(smem + kOffPp + st * 8192 + sw128_offset(i, wh * 4 + c)) =
-                            make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
-                    }
+                    for (int jj = 0; jj < 8; ++jj) o[jj] = (j0 + jj) <= i ? __uint_as_float(r[jj]) * sce : 0.f;
+                    *reinterpret_cast<uint4*>(smem + kOffPp + st * 8192 + sw128_offset(i, wh * 4 + c8)) =
+                        make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
                 }
             }
+            tc_fence_before_sync();
+            mbar_arrive(&bars[kKqFree]);
             kbar();
             if (!fast) {   // rare: chunk decay below e^-60 -> per-element exp(Gamma_i - Gamma_j) instead of folded factors
                 const float* Gm = sGam + st * 64;
@@ -402,15 +399,16 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             }
             kbar();
             // block merges; warp 7 has no 16x16 merge tile and scans the gates of chunk n+1 meanwhile
+            if (warp == 7) kbar_mid_arrive();    // middle barrier of the 16x16 merge: warp 7 is not waited for
             if (warp == 7 && n + 1 < NC)
                 gate_scan(sG + (st ^ 1) * 64, sBt + (st ^ 1) * 64, sGam + (st ^ 1) * 64, sE + (st ^ 1) * 64, sCj + (st ^ 1) * 64,
                           sKd + (st ^ 1) * 64, sFast + (st ^ 1), sOfac + ((n + 1) & 3) * 64, sPost + ((n + 1) & 3), sPre + ((n + 1) & 3),
                           scale, lane);
-            tri_merge<16, 2>(sA, sY, warp, lane);
-            tri_merge<32, 1>(sA, sY, warp, lane);
+            tri_merge<16, 2, true>(sA, sY, warp, lane);
+            tri_merge<32, 1, false>(sA, sY, warp, lane);
             {   // T' = X diag(c) -> bf16, K-major swizzled rows (thread: 4 consecutive columns of one row, 4 tasks)
                 const float* cjS = sCj + st * 64;
-#pragma unroll
+#pragma unroll 1
                 for (int it = 0; it < 4; ++it) {
                     const int task = it * kKThreads + tid, i = task >> 4, q4 = task & 15;
                     const float4 x = *reinterpret_cast<const float4*>(sA + i * kPitchA + q4 * 4);
@@ -433,7 +431,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
-#pragma unroll
+#pragma unroll 1
                 for (int ks = 0; ks < 4; ++ks) {
                     if (ks * 16 <= ng * 32 + 31) {          // T' is lower triangular: j <= i
                         uint32_t af[4], bf0[4], bf1[4];
@@ -448,9 +446,9 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                         }
                         ldmatrix_x4(bf0, aT + sw128_offset(ng * 32 + ((lane >> 4) & 1) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
                         ldmatrix_x4(bf1, aT + sw128_offset(ng * 32 + 16 + ((lane >> 4) & 1) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
-                        mma_bf16(acc[0], af, bf0[0], bf0[1]);
-                        mma_bf16(acc[1], af, bf0[2], bf0[3]);
-                        mma_bf16(acc[2], af, bf1[0], bf1[1]);
+                        if (ks * 16 <= ng * 32 + 7) mma_bf16(acc[0], af, bf0[0], bf0[1]);
+                        if (ks * 16 <= ng * 32 + 15) mma_bf16(acc[1], af, bf0[2], bf0[3]);
+                        if (ks * 16 <= ng * 32 + 23) mma_bf16(acc[2], af, bf1[0], bf1[1]);
                         mma_bf16(acc[3], af, bf1[2], bf1[3]);
                     }
                 }
@@ -487,35 +485,33 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 }
                 tmem_wait_st();
             }
-            // drain the readout of chunk m: O^T -> bf16 -> staging [2][tok][64] -> TMA store (rows past the frame are clipped)
+            // drain the readout of chunk m: O^T -> * (scale e_i) -> bf16 -> staging [2][tok][64] -> TMA store
+            // (rows past the frame are clipped by the tensor map)
             auto readout = [&](int m) {
-                uint32_t r0[32], r1[32];
                 mbar_wait(&bars[kOFull + hh], (uint32_t)m & 1u);
                 tc_fence_after_sync();
-                tmem_ld32(lane_addr + kColO + hh * 64, r0);
-                tmem_ld32(lane_addr + kColO + hh * 64 + 32, r1);
-                tmem_wait_ld();
-                tc_fence_before_sync();
-                mbar_arrive(&bars[kOFree + hh]);
                 if (stid == 0) tma_store_wait_read0();      // previous readout has left the staging buffer
                 named_bar_sync(bar_id, 128);
-                const float4* of4 = reinterpret_cast<const float4*>(sOfac + (m & 3) * 64);   // row factor scale e_i (or 1)
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 c = of4[j4];
-                    ost[(j4 * 4 + 0) * 64] = __float2bfloat16_rn(__uint_as_float(r0[j4 * 4 + 0]) * c.x);
-                    ost[(j4 * 4 + 1) * 64] = __float2bfloat16_rn(__uint_as_float(r0[j4 * 4 + 1]) * c.y);
-                    ost[(j4 * 4 + 2) * 64] = __float2bfloat16_rn(__uint_as_float(r0[j4 * 4 + 2]) * c.z);
-                    ost[(j4 * 4 + 3) * 64] = __float2bfloat16_rn(__uint_as_float(r0[j4 * 4 + 3]) * c.w);
+                const float* of = sOfac + (m & 3) * 64;
+#pragma unroll 1
+                for (int c8 = 0; c8 < 8; ++c8) {
+                    uint32_t r[8];
+                    tmem_ld8(lane_addr + kColO + hh * 64 + c8 * 8, r);
+                    tmem_wait_ld();
+                    const float4 c0 = *reinterpret_cast<const float4*>(of + c8 * 8);
+                    const float4 c1 = *reinterpret_cast<const float4*>(of + c8 * 8 + 4);
+                    __nv_bfloat16* o8 = ost + c8 * 8 * 64;
+                    o8[0 * 64] = __float2bfloat16_rn(__uint_as_float(r[0]) * c0.x);
+                    o8[1 * 64] = __float2bfloat16_rn(__uint_as_float(r[1]) * c0.y);
+                    o8[2 * 64] = __float2bfloat16_rn(__uint_as_float(r[2]) * c0.z);
+                    o8[3 * 64] = __float2bfloat16_rn(__uint_as_float(r[3]) * c0.w);
+                    o8[4 * 64] = __float2bfloat16_rn(__uint_as_float(r[4]) * c1.x);
+                    o8[5 * 64] = __float2bfloat16_rn(__uint_as_float(r[5]) * c1.y);
+                    o8[6 * 64] = __float2bfloat16_rn(__uint_as_float(r[6]) * c1.z);
+                    o8[7 * 64] = __float2bfloat16_rn(__uint_as_float(r[7]) * c1.w);
                 }
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 c = of4[8 + j4];
-                    ost[(32 + j4 * 4 + 0) * 64] = __float2bfloat16_rn(__uint_as_float(r1[j4 * 4 + 0]) * c.x);
-                    ost[(32 + j4 * 4 + 1) * 64] = __float2bfloat16_rn(__uint_as_float(r1[j4 * 4 + 1]) * c.y);
-                    ost[(32 + j4 * 4 + 2) * 64] = __float2bfloat16_rn(__uint_as_float(r1[j4 * 4 + 2]) * c.z);
-                    ost[(32 + j4 * 4 + 3) * 64] = __float2bfloat16_rn(__uint_as_float(r1[j4 * 4 + 3]) * c.w);
-                }
+                tc_fence_before_sync();
+                mbar_arrive(&bars[kOFree + hh]);
                 fence_proxy_async_smem();
                 named_bar_sync(bar_id, 128);
                 if (stid == 0) {
@@ -531,20 +527,22 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 tc_fence_after_sync();
                 {   // S_n = post_{n-1} * accumulator;  Sb = bf16(S_n) (operand copy);  accumulator <- pre_n * S_n
                     const float post = n >= 1 ? sPost[(n - 1) & 3] : 1.f, pre = sPre[n & 3];
-                    uint32_t r[32], pk[32];
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        tmem_ld32(lane_addr + kColS + hh * 64 + half * 32, r);
+#pragma unroll 1
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        uint32_t r[8], pk[4];
+                        tmem_ld8(lane_addr + kColS + hh * 64 + c8 * 8, r);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * post);
+                        for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * post);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[half * 16 + j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                        for (int j = 0; j < 4; ++j) pk[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                        tmem_st4(lane_addr + kColSb + hh * 32 + c8 * 4, pk);
+                        if (pre != 1.f) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * pre);
-                        tmem_st32(lane_addr + kColS + hh * 64 + half * 32, r);
+                            for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * pre);
+                        }
+                        if (pre != 1.f || post != 1.f) tmem_st8(lane_addr + kColS + hh * 64 + c8 * 8, r);
                     }
-                    tmem_st32(lane_addr + kColSb + hh * 32, pk);
                     tmem_wait_st();
                 }
                 tc_fence_before_sync();
@@ -552,16 +550,17 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 if (n >= 1) readout(n - 1);                                         // in the shadow of the Vn MMAs
                 mbar_wait(&bars[kVnFull + hh], (uint32_t)n & 1u);
                 tc_fence_after_sync();
-                {   // Vnb = bf16(Vn^T) written over the first half of Vn (TMEM A-operand)
-                    uint32_t r[32], pk[32];
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        tmem_ld32(lane_addr + kColVn + hh * 64 + half * 32, r);
+                {   // Vnb = bf16(Vn^T) written over the first half of Vn (TMEM A-operand): column block c8 of
+                    // the fp32 tile is read before the (earlier) bf16 columns 4 c8 .. 4 c8 + 3 are overwritten
+#pragma unroll 1
+                    for (int c8 = 0; c8 < 8; ++c8) {
+                        uint32_t r[8], pk[4];
+                        tmem_ld8(lane_addr + kColVn + hh * 64 + c8 * 8, r);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[half * 16 + j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                        for (int j = 0; j < 4; ++j) pk[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                        tmem_st4(lane_addr + kColVn + hh * 64 + c8 * 4, pk);
                     }
-                    tmem_st32(lane_addr + kColVn + hh * 64, pk);
                     tmem_wait_st();
                 }
                 tc_fence_before_sync();
@@ -701,7 +700,10 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
         attr_err = cudaFuncSetAttribute(gdr_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (attr_err != cudaSuccess) return (int)attr_err;
     }
-    const bool flat = p.frame_tokens <= 0 || (p.flags & GDKVM_FLAG_FLAT_CHUNKS);
+    // frame-aligned chunks when frames are whole 64-token chunks (or when asked for); otherwise tile the
+    // flat token stream: identical results (token-causal recurrence), no zero-padded rows to process
+    const bool flat = p.frame_tokens <= 0 || (p.flags & GDKVM_FLAG_FLAT_CHUNKS) ||
+                      (p.frame_tokens % 64 != 0 && !(p.flags & GDKVM_FLAG_FRAME_CHUNKS));
     const int C = flat ? p.T : p.frame_tokens;
     const int F = p.T / C;
     const uint64_t B = p.B, H = p.H, V = p.V;

@@ -48,6 +48,10 @@ enum GdkvmStatus {
 #define GDKVM_FLAG_FLAT_CHUNKS     0x4u /* chunked kernel: tile the flat token stream in 64-token
                                            chunks instead of frame-aligned chunks (same results,
                                            no 49->64 padding work)                                    */
+#define GDKVM_FLAG_FRAME_CHUNKS    0x8u /* chunked kernel: always one chunk per frame (sub-chunks of
+                                           64 for longer frames).  Default: frame-aligned when
+                                           frame_tokens is a multiple of 64, flat tiling otherwise --
+                                           token-causal semantics make the two exactly equivalent     */
 
 /*
  * One forward call of the memory module over a batch of clips.
