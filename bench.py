@@ -222,11 +222,13 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = gdkvm_b200.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()          # cudaProfilerStart: `ncu --profile-from-start off` sees the timed region only
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
+    torch.cuda.profiler.stop()
     launches = gdkvm_b200.launch_count() - launches0
     ms_total = ev0.elapsed_time(ev1)
     tmax = torch.tensor([ms_total], device=dev)
@@ -339,9 +341,10 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16 I/O, fp32 state/accumulate", "data": "synthetic",
+        "dtype": "bf16", "data": "synthetic",
         "config": {"workload": W["name"], "clips_per_gpu": B, "frames": W["frames"], "frame_tokens": C, "heads": H,
                    "d_k": K, "d_v": V, "tokens_per_clip": T, "flags": args.flags, "kernel": kernel,
+                   "arithmetic": "bf16 q/k/v/o and tensor-core operands, fp32 state/accumulators/gates",
                    "l2": "inputs+outputs per step (4.2 GB) exceed the 126 MB L2; no flush needed",
                    "sharding": "clips x heads across ranks, no collective on the hot path"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),

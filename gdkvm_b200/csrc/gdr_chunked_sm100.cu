@@ -64,8 +64,8 @@ constexpr uint32_t kOffOst = kOffTp + 16384;     // readout staging, per value h
 constexpr uint32_t kOffA = kOffOst + 32768;      // fp32 solve matrix
 constexpr uint32_t kOffY = kOffA + 64 * kPitchA * 4;
 constexpr uint32_t kOffF = kOffY + 32 * kPitchY * 4;
-//   floats: g[2][64] beta[2][64] Gam[2][64] E[2][64] Cj[2][64] Kd[2][64] Ofac[4][64] post[4] pre[4] fast[2] pad[2]
-constexpr uint32_t kNumFloats = 16 * 64 + 12;
+//   floats: g[2][64] beta[2][64] Gam[2][64] E[4][64] Cj[2][64] Kd[2][64] Ofac[4][64] post[4] pre[4] fast[2] pad[2]
+constexpr uint32_t kNumFloats = 18 * 64 + 12;
 constexpr uint32_t kOffBar = kOffF + kNumFloats * 4;
 constexpr uint32_t kNumBars = 26;
 constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;   // + tmem slot + alignment slack
@@ -84,8 +84,8 @@ enum Bar : int {
     kTmaFull = 0,    // [2] tiles of a chunk landed                      (tx)      -> issuer K, K group
     kKqFull = 2,     //     [K;Q]K^T accumulators complete                (commit)  -> K group
     kKqFree = 3,     //     [K;Q]K^T accumulators drained                 (256)     -> issuer K
-    kTpReady = 4,    // [2] T' (and K~, Q~, K', P) written                (1)       -> issuer S (U)
-    kKsideFull = 6,  // [2] W^T operand + gamma published (K side done)   (1)       -> issuer S, state groups
+    kTpReady = 4,    // [2] K side done: T', P, decay factors published   (1)       -> issuer S (U), state groups (W)
+    kKsideFull = 6,  // [2] W^T operand written by the state groups       (128 NH)  -> issuer S
     kKsideEmpty = 8, // [2] every MMA of the chunk completed              (commit)  -> K group (operand buffers free)
     kD1Done = 10,    //     tile stage no longer read by any MMA          (commit)  -> issuer K (TMA refill)
     kSbReady = 11,   // [2] per half: Sb + decayed S in TMEM              (128)     -> issuer S
@@ -96,6 +96,23 @@ enum Bar : int {
     kOFree = 21,     // [2] per half: readout accumulators drained        (128)     -> issuer S
     kKpFull = 23,    // [2] second copy of the K tile landed               (tx)      -> issuer S (state update), K group (slow path)
 };
+
+// ---- optional phase timers (build with -DGDKVM_PHASE_TIMERS: scripts/phase_timers.py) ----
+#ifdef GDKVM_PHASE_TIMERS
+__device__ unsigned long long g_phase_cycles[64];
+#define PT_DECL long long pt_prev = clock64();
+#define PT(slot, cond)                                                                 \
+    do {                                                                               \
+        if (blockIdx.x == 0 && (cond)) {                                               \
+            const long long pt_now = clock64();                                        \
+            atomicAdd(&g_phase_cycles[slot], (unsigned long long)(pt_now - pt_prev));  \
+            pt_prev = pt_now;                                                          \
+        }                                                                              \
+    } while (0)
+#else
+#define PT_DECL
+#define PT(slot, cond) do { } while (0)
+#endif
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -218,6 +235,46 @@ __device__ __forceinline__ void gate_scan(const float* gS, const float* btS, flo
     if (lane == 0) { *post = fast ? gam : 1.f; *pre = fast ? 1.f : gam; *sFast = fast ? 1.f : 0.f; }
 }
 
+// One 16 (key dims d) x 32 (tokens i) unit of  W^T[d][i] = sum_j (K[j][d] e_j) T'[i][j]  in registers:
+// bf16 mma.sync with ldmatrix from the 128B-swizzled K tile (transposed) and T' tile; e_j is applied to
+// the K fragments; the result is written as the bf16 MN-major operand rows of the Vn correction MMA
+// (row = key dim d, contiguous over tokens i).  T' is lower triangular: slices with j > i are skipped.
+__device__ __forceinline__ void w_unit_mma(uint32_t aK, uint32_t aT, uint8_t* wt, const float* eS, int mt, int ng, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+#pragma unroll 1
+    for (int ks = 0; ks < 4; ++ks) {
+        if (ks * 16 <= ng * 32 + 31) {
+            uint32_t af[4], bf0[4], bf1[4];
+            ldmatrix_x4_trans(af, aK + sw128_offset(ks * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, mt * 2 + ((lane >> 3) & 1)));
+            {   // K~ = K e_j: fragment registers hold tokens j = 16 ks + 2t (+1) and + 8
+                const float2 e01 = *reinterpret_cast<const float2*>(eS + ks * 16 + 2 * t);
+                const float2 e89 = *reinterpret_cast<const float2*>(eS + ks * 16 + 2 * t + 8);
+                af[0] = pack_bf16(__uint_as_float(af[0] << 16) * e01.x, __uint_as_float(af[0] & 0xffff0000u) * e01.y);
+                af[1] = pack_bf16(__uint_as_float(af[1] << 16) * e01.x, __uint_as_float(af[1] & 0xffff0000u) * e01.y);
+                af[2] = pack_bf16(__uint_as_float(af[2] << 16) * e89.x, __uint_as_float(af[2] & 0xffff0000u) * e89.y);
+                af[3] = pack_bf16(__uint_as_float(af[3] << 16) * e89.x, __uint_as_float(af[3] & 0xffff0000u) * e89.y);
+            }
+            ldmatrix_x4(bf0, aT + sw128_offset(ng * 32 + ((lane >> 4) & 1) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
+            ldmatrix_x4(bf1, aT + sw128_offset(ng * 32 + 16 + ((lane >> 4) & 1) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
+            if (ks * 16 <= ng * 32 + 7) mma_bf16(acc[0], af, bf0[0], bf0[1]);
+            if (ks * 16 <= ng * 32 + 15) mma_bf16(acc[1], af, bf0[2], bf0[3]);
+            if (ks * 16 <= ng * 32 + 23) mma_bf16(acc[2], af, bf1[0], bf1[1]);
+            mma_bf16(acc[3], af, bf1[2], bf1[3]);
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const int i0 = ng * 32 + nt * 8 + 2 * t;
+        *reinterpret_cast<uint32_t*>(wt + sw128_offset(mt * 16 + g, i0 >> 3) + (i0 & 7) * 2) = pack_bf16(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<uint32_t*>(wt + sw128_offset(mt * 16 + g + 8, i0 >> 3) + (i0 & 7) * 2) = pack_bf16(acc[nt][2], acc[nt][3]);
+    }
+}
+
 // four 128x64x16 tcgen05 MMAs covering K = 64; descriptors advance by a fixed step per K slice
 __device__ __forceinline__ void umma4_ss(uint32_t d, uint64_t a, uint32_t astep, uint64_t bdesc, uint32_t bstep, uint32_t idesc, bool acc0) {
 #pragma unroll
@@ -242,8 +299,8 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     float* sG = reinterpret_cast<float*>(smem + kOffF);   // [2][64] log gates of the chunk in each stage
     float* sBt = sG + 128;                                // [2][64] beta
     float* sGam = sBt + 128;                              // [2][64] Gamma_i (inclusive cumsum of g)
-    float* sE = sGam + 128;                               // [2][64] exp(Gamma_i)
-    float* sCj = sE + 128;                                // [2][64] column factor of T': f_j beta_j (fast) | beta_j (slow)
+    float* sE = sGam + 128;                               // [4][64] exp(Gamma_i) of chunk n in slot n & 3
+    float* sCj = sE + 256;                                // [2][64] column factor of T': f_j beta_j (fast) | beta_j (slow)
     float* sKd = sCj + 128;                               // [2][64] row factor of K':    gamma (fast) | exp(Gamma_last - Gamma_i) (slow)
     float* sOfac = sKd + 128;                             // [4][64] readout row factor of chunk n in slot n & 3: scale e_i | 1
     float* sPost = sOfac + 256;                           // [4] factor applied to S AFTER chunk n's accumulate: gamma | 1
@@ -262,7 +319,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         mbar_init(&bars[kTmaFull], 1); mbar_init(&bars[kTmaFull + 1], 1);
         mbar_init(&bars[kKqFull], 1); mbar_init(&bars[kKqFree], kKThreads);
         mbar_init(&bars[kTpReady], 1); mbar_init(&bars[kTpReady + 1], 1);
-        mbar_init(&bars[kKsideFull], 1); mbar_init(&bars[kKsideFull + 1], 1);
+        mbar_init(&bars[kKsideFull], 128 * NH); mbar_init(&bars[kKsideFull + 1], 128 * NH);
         mbar_init(&bars[kKsideEmpty], 1); mbar_init(&bars[kKsideEmpty + 1], 1);
         mbar_init(&bars[kD1Done], 1);
         mbar_init(&bars[kKpFull], 1); mbar_init(&bars[kKpFull + 1], 1);
@@ -306,14 +363,15 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         };
         if (tid < 64) { float gv, bv; load_gates(0, gv, bv); sG[tid] = gv; sBt[tid] = bv; }
         kbar();
-        if (warp == 7) gate_scan(sG, sBt, sGam, sE, sCj, sKd, sFast, sOfac, sPost, sPre, scale, lane);
+        if (warp == 7) gate_scan(sG, sBt, sGam, sE, sCj, sKd, sFast, sOfac, sPost, sPre, scale, lane);   // chunk 0 -> slot 0
         kbar();
 
+        PT_DECL
         for (int n = 0; n < NC; ++n) {
             const int st = n & 1;
             uint8_t* sp = smem + st * kStageBytes;
             const float* btS = sBt + st * 64;
-            const float* eS = sE + st * 64;
+            const float* eS = sE + (n & 3) * 64;
             float g_next = 0.f, b_next = 0.f;
             if (n + 1 < NC && tid < 64) load_gates(n + 1, g_next, b_next);
             // operand buffers of this stage are free once every MMA of chunk n-2 has completed
@@ -324,6 +382,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             mbar_wait(&bars[kTmaFull + st], (uint32_t)(n >> 1) & 1u);   // tiles visible to this thread's loads
             mbar_wait(&bars[kKqFull], (uint32_t)n & 1u);
             tc_fence_after_sync();
+            PT(0, tid == 0);   // waits: buffers free, tiles landed, [K;Q]K^T done
 #pragma unroll 1
             for (int c8 = 0; c8 < 4; ++c8) {      // 8 accumulator columns per step keeps the loop body in the L0 i-cache
                 uint32_t r[8];
@@ -350,7 +409,9 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             }
             tc_fence_before_sync();
             mbar_arrive(&bars[kKqFree]);
+            PT(1, tid == 0);   // gating (own work)
             kbar();
+            PT(2, tid == 0);   // gating (barrier wait)
             if (!fast) {   // rare: chunk decay below e^-60 -> per-element exp(Gamma_i - Gamma_j) instead of folded factors
                 const float* Gm = sGam + st * 64;
 #pragma unroll 1
@@ -397,15 +458,18 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 for (int i = 0; i < 16; ++i) Ab[i * kPitchA + c] = x[i];
                 if (n + 1 < NC) { sG[(st ^ 1) * 64 + tid] = g_next; sBt[(st ^ 1) * 64 + tid] = b_next; }
             }
+            PT(3, tid == 0);   // diagonal 16x16 inverses (own work)
             kbar();
             // block merges; warp 7 has no 16x16 merge tile and scans the gates of chunk n+1 meanwhile
             if (warp == 7) kbar_mid_arrive();    // middle barrier of the 16x16 merge: warp 7 is not waited for
             if (warp == 7 && n + 1 < NC)
-                gate_scan(sG + (st ^ 1) * 64, sBt + (st ^ 1) * 64, sGam + (st ^ 1) * 64, sE + (st ^ 1) * 64, sCj + (st ^ 1) * 64,
+                gate_scan(sG + (st ^ 1) * 64, sBt + (st ^ 1) * 64, sGam + (st ^ 1) * 64, sE + ((n + 1) & 3) * 64, sCj + (st ^ 1) * 64,
                           sKd + (st ^ 1) * 64, sFast + (st ^ 1), sOfac + ((n + 1) & 3) * 64, sPost + ((n + 1) & 3), sPre + ((n + 1) & 3),
                           scale, lane);
             tri_merge<16, 2, true>(sA, sY, warp, lane);
+            PT(4, tid == 0);   // 16x16 merges
             tri_merge<32, 1, false>(sA, sY, warp, lane);
+            PT(5, tid == 0);   // 32x32 merge
             {   // T' = X diag(c) -> bf16, K-major swizzled rows (thread: 4 consecutive columns of one row, 4 tasks)
                 const float* cjS = sCj + st * 64;
 #pragma unroll 1
@@ -419,50 +483,9 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             }
             fence_proxy_async_smem();
             kbar();
+            PT(6, tid == 0);   // T' conversion
             if (tid == 0) mbar_arrive(&bars[kTpReady + st]);
 
-            // W^T[d][i] = sum_j K~[j][d] T'[i][j] in registers (bf16 mma.sync, ldmatrix from the swizzled tiles)
-            // -> bf16 MN-major operand rows (row = key dim d, contiguous over tokens i)
-            {
-                const int mt = warp & 3, ng = warp >> 2, g = lane >> 2, t = lane & 3;
-                const uint32_t aK = sbase + st * kStageBytes + kOffKt, aT = sbase + kOffTp + st * 8192;
-                float acc[4][4];
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
-#pragma unroll 1
-                for (int ks = 0; ks < 4; ++ks) {
-                    if (ks * 16 <= ng * 32 + 31) {          // T' is lower triangular: j <= i
-                        uint32_t af[4], bf0[4], bf1[4];
-                        ldmatrix_x4_trans(af, aK + sw128_offset(ks * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, mt * 2 + ((lane >> 3) & 1)));
-                        {   // K~ = K e_j: fragment registers hold tokens j = 16 ks + 2t (+1) and + 8
-                            const float2 e01 = *reinterpret_cast<const float2*>(eS + ks * 16 + 2 * t);
-                            const float2 e89 = *reinterpret_cast<const float2*>(eS + ks * 16 + 2 * t + 8);
-                            af[0] = pack_bf16(__uint_as_float(af[0] << 16) * e01.x, __uint_as_float(af[0] & 0xffff0000u) * e01.y);
-                            af[1] = pack_bf16(__uint_as_float(af[1] << 16) * e01.x, __uint_as_float(af[1] & 0xffff0000u) * e01.y);
-                            af[2] = pack_bf16(__uint_as_float(af[2] << 16) * e89.x, __uint_as_float(af[2] & 0xffff0000u) * e89.y);
-                            af[3] = pack_bf16(__uint_as_float(af[3] << 16) * e89.x, __uint_as_float(af[3] & 0xffff0000u) * e89.y);
-                        }
-                        ldmatrix_x4(bf0, aT + sw128_offset(ng * 32 + ((lane >> 4) & 1) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
-                        ldmatrix_x4(bf1, aT + sw128_offset(ng * 32 + 16 + ((lane >> 4) & 1) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
-                        if (ks * 16 <= ng * 32 + 7) mma_bf16(acc[0], af, bf0[0], bf0[1]);
-                        if (ks * 16 <= ng * 32 + 15) mma_bf16(acc[1], af, bf0[2], bf0[3]);
-                        if (ks * 16 <= ng * 32 + 23) mma_bf16(acc[2], af, bf1[0], bf1[1]);
-                        mma_bf16(acc[3], af, bf1[2], bf1[3]);
-                    }
-                }
-                uint8_t* wt = smem + kOffWt + st * 8192;
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) {
-                    const int i0 = ng * 32 + nt * 8 + 2 * t;
-                    *reinterpret_cast<uint32_t*>(wt + sw128_offset(mt * 16 + g, i0 >> 3) + (i0 & 7) * 2) = pack_bf16(acc[nt][0], acc[nt][1]);
-                    *reinterpret_cast<uint32_t*>(wt + sw128_offset(mt * 16 + g + 8, i0 >> 3) + (i0 & 7) * 2) = pack_bf16(acc[nt][2], acc[nt][3]);
-                }
-            }
-            fence_proxy_async_smem();
-            kbar();
-            if (tid == 0) mbar_arrive(&bars[kKsideFull + st]);
         }
     } else if (warp < 16) {
         // =========================================================================================
@@ -473,7 +496,6 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
             const int vcol = hh * 128 + wq * 32 + lane;
             const int bar_id = 2 + hh;
-            __nv_bfloat16* ost = reinterpret_cast<__nv_bfloat16*>(smem + kOffOst + hh * 16384) + (wq >> 1) * 4096 + ((wq & 1) * 32 + lane);
             {   // initial state -> TMEM
                 uint32_t r[32];
                 const float* s0 = p.initial_state ? p.initial_state + (int64_t)chain * 64 * V + vcol : nullptr;
@@ -485,30 +507,39 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 }
                 tmem_wait_st();
             }
-            // drain the readout of chunk m: O^T -> * (scale e_i) -> bf16 -> staging [2][tok][64] -> TMA store
+            // drain the readout of chunk m: O^T accumulators in mma-fragment layout (16x256b TMEM loads) -> * scale e_i
+            // -> bf16 pairs -> stmatrix.trans into the 128B-swizzled staging tile [2][tok][64] -> TMA store
             // (rows past the frame are clipped by the tensor map)
+            PT_DECL
             auto readout = [&](int m) {
                 mbar_wait(&bars[kOFull + hh], (uint32_t)m & 1u);
                 tc_fence_after_sync();
+                PT(23, tid == 256);   // wait: readout accumulators (after Vnb -> state update + intra-chunk MMAs)
                 if (stid == 0) tma_store_wait_read0();      // previous readout has left the staging buffer
                 named_bar_sync(bar_id, 128);
-                const float* of = sOfac + (m & 3) * 64;
-#pragma unroll 1
-                for (int c8 = 0; c8 < 8; ++c8) {
-                    uint32_t r[8];
-                    tmem_ld8(lane_addr + kColO + hh * 64 + c8 * 8, r);
+                PT(24, tid == 256);   // wait: staging buffer free + group barrier
+                const float* of = sOfac + (m & 3) * 64 + 2 * (lane & 3);
+                const uint32_t ost_half = sbase + kOffOst + hh * 16384;
+#pragma unroll
+                for (int grp = 0; grp < 2; ++grp) {
+                    uint32_t r[32];
+                    tmem_ld_16x256b_x8(tmem + ((uint32_t)(wq * 32 + grp * 16) << 16) + kColO + hh * 64, r);
                     tmem_wait_ld();
-                    const float4 c0 = *reinterpret_cast<const float4*>(of + c8 * 8);
-                    const float4 c1 = *reinterpret_cast<const float4*>(of + c8 * 8 + 4);
-                    __nv_bfloat16* o8 = ost + c8 * 8 * 64;
-                    o8[0 * 64] = __float2bfloat16_rn(__uint_as_float(r[0]) * c0.x);
-                    o8[1 * 64] = __float2bfloat16_rn(__uint_as_float(r[1]) * c0.y);
-                    o8[2 * 64] = __float2bfloat16_rn(__uint_as_float(r[2]) * c0.z);
-                    o8[3 * 64] = __float2bfloat16_rn(__uint_as_float(r[3]) * c0.w);
-                    o8[4 * 64] = __float2bfloat16_rn(__uint_as_float(r[4]) * c1.x);
-                    o8[5 * 64] = __float2bfloat16_rn(__uint_as_float(r[5]) * c1.y);
-                    o8[6 * 64] = __float2bfloat16_rn(__uint_as_float(r[6]) * c1.z);
-                    o8[7 * 64] = __float2bfloat16_rn(__uint_as_float(r[7]) * c1.w);
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float2 c = *reinterpret_cast<const float2*>(of + 8 * q);
+                        pk[2 * q] = pack_bf16(__uint_as_float(r[4 * q]) * c.x, __uint_as_float(r[4 * q + 1]) * c.y);
+                        pk[2 * q + 1] = pack_bf16(__uint_as_float(r[4 * q + 2]) * c.x, __uint_as_float(r[4 * q + 3]) * c.y);
+                    }
+                    // lane l addresses matrix l/8 (token block +(l/16), value rows +8 ((l/8)&1)), memory row = token l%8
+                    const int v0 = wq * 32 + grp * 16 + ((lane >> 3) & 1) * 8;
+                    const uint32_t vaddr = ost_half + (v0 >> 6) * 8192;
+#pragma unroll
+                    for (int q = 0; q < 8; q += 2) {
+                        const int tok = 8 * (q + (lane >> 4)) + (lane & 7);
+                        stmatrix_x4_trans(vaddr + sw128_offset(tok, (v0 & 63) >> 3), pk[2 * q], pk[2 * q + 1], pk[2 * q + 2], pk[2 * q + 3]);
+                    }
                 }
                 tc_fence_before_sync();
                 mbar_arrive(&bars[kOFree + hh]);
@@ -522,49 +553,66 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             };
             for (int n = 0; n < NC; ++n) {
                 const int st = n & 1;
-                mbar_wait(&bars[kKsideFull + st], (uint32_t)(n >> 1) & 1u);       // gamma of chunk n published
+                if (n >= 1) readout(n - 1);                                         // while the K side of chunk n finishes
+                PT(19, tid == 256);   // readout of chunk n-1
+                mbar_wait(&bars[kTpReady + st], (uint32_t)(n >> 1) & 1u);          // K side of chunk n published
+                PT(16, tid == 256);   // wait: K side of chunk n
+                {   // W^T of chunk n: 8 units of 16 key dims x 32 tokens shared by the state warps
+                    const int sw = (warp - 8);                                      // 0 .. 4 NH - 1
+                    for (int u = sw; u < 8; u += 4 * NH)
+                        w_unit_mma(sbase + st * kStageBytes + kOffKt, sbase + kOffTp + st * 8192, smem + kOffWt + st * 8192,
+                                   sE + (n & 3) * 64, u & 3, u >> 2, lane);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&bars[kKsideFull + st]);
+                }
+                PT(22, tid == 256);   // W^T mma.sync
                 if (n >= 1) mbar_wait(&bars[kSReady + hh], (uint32_t)(n - 1) & 1u);
                 tc_fence_after_sync();
+                PT(17, tid == 256);   // wait: state update of chunk n-1
                 {   // S_n = post_{n-1} * accumulator;  Sb = bf16(S_n) (operand copy);  accumulator <- pre_n * S_n
                     const float post = n >= 1 ? sPost[(n - 1) & 3] : 1.f, pre = sPre[n & 3];
-#pragma unroll 1
-                    for (int c8 = 0; c8 < 8; ++c8) {
-                        uint32_t r[8], pk[4];
-                        tmem_ld8(lane_addr + kColS + hh * 64 + c8 * 8, r);
+                    const bool rescale = pre != 1.f || post != 1.f;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t r[32], pk[16];
+                        tmem_ld32(lane_addr + kColS + hh * 64 + half * 32, r);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * post);
+                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * post);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) pk[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-                        tmem_st4(lane_addr + kColSb + hh * 32 + c8 * 4, pk);
-                        if (pre != 1.f) {
+                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+                        tmem_st16(lane_addr + kColSb + hh * 32 + half * 16, pk);
+                        if (rescale) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * pre);
+                            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * pre);
+                            tmem_st32(lane_addr + kColS + hh * 64 + half * 32, r);
                         }
-                        if (pre != 1.f || post != 1.f) tmem_st8(lane_addr + kColS + hh * 64 + c8 * 8, r);
                     }
                     tmem_wait_st();
                 }
                 tc_fence_before_sync();
                 mbar_arrive(&bars[kSbReady + hh]);
-                if (n >= 1) readout(n - 1);                                         // in the shadow of the Vn MMAs
+                PT(18, tid == 256);   // S pass
                 mbar_wait(&bars[kVnFull + hh], (uint32_t)n & 1u);
                 tc_fence_after_sync();
-                {   // Vnb = bf16(Vn^T) written over the first half of Vn (TMEM A-operand): column block c8 of
-                    // the fp32 tile is read before the (earlier) bf16 columns 4 c8 .. 4 c8 + 3 are overwritten
-#pragma unroll 1
-                    for (int c8 = 0; c8 < 8; ++c8) {
-                        uint32_t r[8], pk[4];
-                        tmem_ld8(lane_addr + kColVn + hh * 64 + c8 * 8, r);
-                        tmem_wait_ld();
+                PT(20, tid == 256);   // wait: Vn
+                {   // Vnb = bf16(Vn^T) written over the first half of Vn (TMEM A-operand); both fp32 halves are
+                    // in registers before the bf16 columns overwrite them
+                    uint32_t r0[32], r1[32], pk[32];
+                    tmem_ld32(lane_addr + kColVn + hh * 64, r0);
+                    tmem_ld32(lane_addr + kColVn + hh * 64 + 32, r1);
+                    tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) pk[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-                        tmem_st4(lane_addr + kColVn + hh * 64 + c8 * 4, pk);
+                    for (int j = 0; j < 16; ++j) {
+                        pk[j] = pack_bf16(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+                        pk[16 + j] = pack_bf16(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
                     }
+                    tmem_st32(lane_addr + kColVn + hh * 64, pk);
                     tmem_wait_st();
                 }
                 tc_fence_before_sync();
                 mbar_arrive(&bars[kVnbReady + hh]);
+                PT(21, tid == 256);   // Vnb pass
             }
             readout(NC - 1);
             mbar_wait(&bars[kSReady + hh], (uint32_t)(NC - 1) & 1u);
@@ -626,6 +674,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         // issuer S: the state-side MMAs
         // =========================================================================================
         if (lane == 0) {
+            PT_DECL
 #pragma unroll 1
             for (int n = 0; n < NC; ++n) {
                 const int st = n & 1;
@@ -637,22 +686,27 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 const uint64_t dQt = umma_smem_desc_sw128(aQt, 16, 1024);
                 mbar_wait(&bars[kTpReady + st], (uint32_t)(n >> 1) & 1u);
                 tc_fence_after_sync();
+                PT(32, true);   // issuer S: wait K side
                 for (int hh = 0; hh < NH; ++hh)      // Vn^T[h] = V^T[h] T'^T   (in order after the MMAs of chunk n-1)
                     umma4_ss(tmem + kColVn + hh * 64, umma_smem_desc_sw128(aVt + hh * 16384, 8192, 1024), 128, dTp, 2, kIdMnA, false);
                 mbar_wait(&bars[kKsideFull + st], (uint32_t)(n >> 1) & 1u);
+                PT(33, true);   // issuer S: issue U, wait W^T operand
                 for (int hh = 0; hh < NH; ++hh) {    // Vn^T[h] -= Sb[h] W^T
                     mbar_wait(&bars[kSbReady + hh], (uint32_t)n & 1u);
                     tc_fence_after_sync();
                     umma4_ts(tmem + kColVn + hh * 64, tmem + kColSb + hh * 32, dWt, 128, kIdMnBneg, true);
                     umma_commit(&bars[kVnFull + hh]);
                 }
+                PT(34, true);   // issuer S: wait Sb, issue Vn correction
                 for (int hh = 0; hh < NH; ++hh) {    // O^T[h] = Sb[h] Q~^T
                     if (n >= 1) mbar_wait(&bars[kOFree + hh], (uint32_t)(n - 1) & 1u);
                     tc_fence_after_sync();
                     umma4_ts(tmem + kColO + hh * 64, tmem + kColSb + hh * 32, dQt, 2, kIdKK, false);
                 }
                 umma_commit(&bars[kD1Done]);
+                PT(35, true);   // issuer S: wait O free, issue inter-chunk readout
                 mbar_wait(&bars[kKpFull + st], (uint32_t)(n >> 1) & 1u);
+                PT(36, true);   // issuer S: wait K copy
                 for (int hh = 0; hh < NH; ++hh) {    // S^T[h] += Vnb[h] K' ;  O^T[h] += Vnb[h] P^T
                     mbar_wait(&bars[kVnbReady + hh], (uint32_t)n & 1u);
                     tc_fence_after_sync();
@@ -662,6 +716,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                     umma_commit(&bars[kOFull + hh]);
                 }
                 umma_commit(&bars[kKsideEmpty + st]);
+                PT(37, true);   // issuer S: wait Vnb, issue state update + intra-chunk readout
             }
         }
         __syncwarp();
@@ -676,6 +731,21 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
 bool mult16(int64_t elems) { return (elems * 2) % 16 == 0; }
 
 }  // namespace
+
+#ifdef GDKVM_PHASE_TIMERS
+}  // namespace gdkvm
+// debug-only export of the profiling build: accumulated cycles per phase slot of CTA 0 (and reset)
+extern "C" int gdkvm_debug_phase_cycles(unsigned long long* out, int n) {
+    unsigned long long h[64];
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(h, gdkvm::g_phase_cycles, sizeof h) != cudaSuccess) return -1;
+    for (int i = 0; i < n && i < 64; ++i) out[i] = h[i];
+    unsigned long long z[64] = {0};
+    cudaMemcpyToSymbol(gdkvm::g_phase_cycles, z, sizeof z);
+    return 0;
+}
+namespace gdkvm {
+#endif
 
 bool chunked_supports(const GdkvmGdrParams& p) {
     if (p.io_dtype != GDKVM_BF16 || p.K != 64 || (p.V != 128 && p.V != 256) || p.T <= 0) return false;
@@ -727,7 +797,7 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
         const uint64_t sv[4] = {(uint64_t)p.v_stride[1] * 2, 128, (uint64_t)p.v_stride[1] * 2 * C, (uint64_t)p.v_stride[0] * 2};
         const uint64_t so[4] = {(uint64_t)p.o_stride[1] * 2, 128, (uint64_t)p.o_stride[1] * 2 * C, (uint64_t)p.o_stride[0] * 2};
         int rc = make_tmap(&mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.v, dims, sv, boxv, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc == 0) rc = make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.o, dims, so, boxo, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (rc == 0) rc = make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.o, dims, so, boxo, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc != 0) return (int)cudaErrorInvalidValue;
     }
     gdr_chunk_kernel<<<p.B * p.H, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, C, F);

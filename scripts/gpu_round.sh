@@ -15,7 +15,7 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_
 cat $OUT/${TAG}_bench_ref.json
 CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu $*"
 timeout 600 $CMD > $OUT/${TAG}_plain.log 2>&1 &&
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_list.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 40 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_list.log 2>&1
 timeout 600 $CMD > $OUT/${TAG}_plain2.log 2>&1 &&
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:gdr_ -s 3 -c 1 -o $OUT/${TAG}_prof $CMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu exit $?"; ls -la $OUT

@@ -16,7 +16,7 @@ from oracle.gdr_ref import gdr_recurrent_ref, make_inputs, max_rel_err
 pytestmark = pytest.mark.gpu
 
 TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2}
-RECURRENT, CHUNKED, FLAT = 0x1, 0x2, 0x4
+RECURRENT, CHUNKED, FLAT, FRAME = 0x1, 0x2, 0x4, 0x8
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
 
@@ -42,7 +42,8 @@ def _paths(op, q, k, v, g, beta, C):
     """Every kernel path that can run this problem: forced recurrent, auto, and (if eligible) chunked."""
     paths = [("recurrent", dict(flags=RECURRENT)), ("auto", dict(flags=0))]
     if op.plan(q, k, v, g, beta, frame_tokens=C) == 1:
-        paths += [("chunked", dict(flags=CHUNKED)), ("chunked_flat", dict(flags=CHUNKED | FLAT))]
+        paths += [("chunked", dict(flags=CHUNKED)), ("chunked_flat", dict(flags=CHUNKED | FLAT)),
+                  ("chunked_frame", dict(flags=CHUNKED | FRAME))]
     return paths
 
 
@@ -116,17 +117,24 @@ def test_state_carry_and_strided_views(op, dtype):
     C = 49
     q, k, v, g, beta, S0 = make_inputs(3, 6 * C, 2, 64, 256, seed=8, frame_tokens=C, dtype=dtype)
     qd, kd, vd, gd, bd, sd = _dev(q, k, v, g, beta, S0)
-    for flags in (RECURRENT, 0):
+    # frame-aligned chunking (and the token-recurrent kernel) cuts at the same places in the
+    # segmented and the single call; the default flat 64-token tiling does not (98 is not a multiple
+    # of 64), so it is compared within the tolerance below instead of bit for bit
+    for flags in (RECURRENT, FRAME):
         o, sT = op.gdr_lkva(qd, kd, vd, gd, bd, None, sd, True, C, flags)
         cut = 2 * C
         oa, sa = op.gdr_lkva(qd[:, :cut], kd[:, :cut], vd[:, :cut], gd[:, :cut], bd[:, :cut], None, sd, True, C, flags)
         ob, sb = op.gdr_lkva(qd[:, cut:], kd[:, cut:], vd[:, cut:], gd[:, cut:], bd[:, cut:], None, sa, True, C, flags)
         assert torch.equal(torch.cat([oa, ob], 1), o), flags     # identical chunking => bit-identical
         assert torch.equal(sb, sT), flags
-    mem = op.GDRMemory(frame_tokens=C)
+    mem = op.GDRMemory(frame_tokens=C, flags=FRAME)
     o2, s2 = mem.forward_segments(qd, kd, vd, gd, bd, frames_per_segment=4, initial_state=sd)
     o1, s1 = mem(qd, kd, vd, gd, bd, sd)
     assert torch.equal(o2, o1) and torch.equal(s2, s1)
+    mem = op.GDRMemory(frame_tokens=C)                 # default tiling: equal within the tolerance
+    o3, s3 = mem.forward_segments(qd, kd, vd, gd, bd, frames_per_segment=4, initial_state=sd)
+    o_ref, s_ref = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    assert max_rel_err(o3, o_ref) <= TOL[dtype] and max_rel_err(s3, s_ref) <= TOL[dtype]
 
 
 def test_kat_on_device(op):
