@@ -9,7 +9,8 @@ from typing import List
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libgdkvm_gdr.so")
+# GDKVM_LIB: load another build of the same ABI (profiling / ablation builds made by scripts/)
+LIB_PATH = os.environ.get("GDKVM_LIB") or os.path.join(PKG_DIR, "libgdkvm_gdr.so")
 SOURCES = ["gdr_api.cu", "gdr_recurrent.cu", "gdr_chunked_sm100.cu"]
 
 
@@ -38,6 +39,8 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile every CUDA source for sm_100a into gdkvm_b200/libgdkvm_gdr.so."""
+    if os.environ.get("GDKVM_LIB"):
+        return LIB_PATH
     if force or needs_build():
         cmd = nvcc_command(extra=["-Xptxas", "-v"] if verbose else None)
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -42,6 +42,7 @@
 #include "gdr_common.cuh"
 #include "sm100_ptx.cuh"
 #include "tma_host.h"
+#include "tri_solve.cuh"
 
 namespace gdkvm {
 namespace {
@@ -50,24 +51,24 @@ using namespace sm100;
 
 constexpr int kKThreads = 256;                 // K-side group
 constexpr int kThreads = 18 * 32;              // whole CTA
-constexpr int kPitchA = 68;   // fp32 pitch of the 64x64 solve matrix: conflict-free mma A-fragment loads
-constexpr int kPitchY = 40;   // pitch of the merge scratch: conflict-free mma B-fragment loads
 
 // ---- shared memory map (bytes from a 1024-aligned base) ----
-constexpr uint32_t kStageBytes = 49152;          // Kt 8K | Qt 8K | Vt 32K   (Qt must follow Kt: stacked [K;Q] operand)
-constexpr uint32_t kOffKt = 0, kOffQt = 8192, kOffVt = 16384;
-constexpr uint32_t kOffKp = 2 * kStageBytes;     // K'  [2]  (B of the state update, MN-major)
-constexpr uint32_t kOffPp = kOffKp + 16384;      // P   [2]  (B of the intra-chunk readout, K-major)
+// Two TMA rings with different lifetimes: the K|Q tiles of a chunk live from the K side of the chunk (one
+// chunk ahead) to its state update, the V tile only until U = V^T T'^T has been formed.
+constexpr uint32_t kKqSlots = 3, kKqSlotBytes = 16384;   // Kt 8K | Qt 8K   (Qt must follow Kt: stacked [K;Q] operand)
+constexpr uint32_t kOffKq = 0;
+constexpr uint32_t kOffV = kKqSlots * kKqSlotBytes;       // V ring: [2 slots][2 value halves][2 x 64 values][64 tok][64] bf16
+constexpr uint32_t kVSlotBytes = 32768;
+constexpr uint32_t kOffPp = kOffV + 2 * kVSlotBytes;      // P   [2]  (B of the intra-chunk readout, K-major)
 constexpr uint32_t kOffWt = kOffPp + 16384;      // W^T [2]  (B of the state correction, MN-major)
 constexpr uint32_t kOffTp = kOffWt + 16384;      // T'  [2]  (B of U / W, K-major)
 constexpr uint32_t kOffOst = kOffTp + 16384;     // readout staging, per value half [2][64 tok][64] bf16
-constexpr uint32_t kOffA = kOffOst + 32768;      // fp32 solve matrix
-constexpr uint32_t kOffY = kOffA + 64 * kPitchA * 4;
-constexpr uint32_t kOffF = kOffY + 32 * kPitchY * 4;
-//   floats: g[2][64] beta[2][64] Gam[2][64] E[4][64] Cj[2][64] Kd[2][64] Ofac[4][64] post[4] pre[4] fast[2] pad[2]
+constexpr uint32_t kOffH = kOffOst + 32768;      // fp16 solve matrix (128B-swizzled rows, tri_solve.cuh)
+constexpr uint32_t kOffF = kOffH + 8192;
+//   floats: beta[2][64] Gam[2][64] E[4][64] Cj[2][64] Kd[4][64] Ofac[4][64] post[4] pre[4] fast[4]
 constexpr uint32_t kNumFloats = 18 * 64 + 12;
 constexpr uint32_t kOffBar = kOffF + kNumFloats * 4;
-constexpr uint32_t kNumBars = 26;
+constexpr uint32_t kNumBars = 27;
 constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;   // + tmem slot + alignment slack
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
@@ -81,47 +82,57 @@ constexpr uint32_t kTmemCols = 512;
 
 // ---- mbarrier slots ----
 enum Bar : int {
-    kTmaFull = 0,    // [2] tiles of a chunk landed                      (tx)      -> issuer K, K group
-    kKqFull = 2,     //     [K;Q]K^T accumulators complete                (commit)  -> K group
+    kKqTile = 0,     // [3] K|Q tiles of a chunk landed                  (tx)      -> issuer K, K group
+    kKqFull = 10,     //     [K;Q]K^T accumulators complete                (commit)  -> K group
     kKqFree = 3,     //     [K;Q]K^T accumulators drained                 (256)     -> issuer K
     kTpReady = 4,    // [2] K side done: T', P, decay factors published   (1)       -> issuer S (U), state groups (W)
     kKsideFull = 6,  // [2] W^T operand written by the state groups       (128 NH)  -> issuer S
     kKsideEmpty = 8, // [2] every MMA of the chunk completed              (commit)  -> K group (operand buffers free)
-    kD1Done = 10,    //     tile stage no longer read by any MMA          (commit)  -> issuer K (TMA refill)
     kSbReady = 11,   // [2] per half: Sb + decayed S in TMEM              (128)     -> issuer S
     kVnFull = 13,    // [2] per half: Vn^T complete                       (commit)  -> state group
     kVnbReady = 15,  // [2] per half: Vnb in TMEM                         (128)     -> issuer S
     kSReady = 17,    // [2] per half: state update complete               (commit)  -> state group
     kOFull = 19,     // [2] per half: readout accumulators complete       (commit)  -> state group
     kOFree = 21,     // [2] per half: readout accumulators drained        (128)     -> issuer S
-    kKpFull = 23,    // [2] second copy of the K tile landed               (tx)      -> issuer S (state update), K group (slow path)
+    kVTile = 23,     // [2][2] V tile of a chunk, per value half         (tx)      -> issuer S (U)
 };
 
 // ---- optional phase timers (build with -DGDKVM_PHASE_TIMERS: scripts/phase_timers.py) ----
 #ifdef GDKVM_PHASE_TIMERS
+// g_phase_cycles[slot]: cycles accumulated per phase; g_phase_trace[slot][c]: clock64 at the END of the phase
+// for chunks kTraceFirst + c (a steady-state window), which gives a cross-role timeline of CTA 0.
 __device__ unsigned long long g_phase_cycles[64];
+__device__ long long g_phase_trace[64][8];
+constexpr int kTraceFirst = 40;
 #define PT_DECL long long pt_prev = clock64();
-#define PT(slot, cond)                                                                 \
+#define PT(slot, cond, chunk)                                                          \
     do {                                                                               \
         if (blockIdx.x == 0 && (cond)) {                                               \
             const long long pt_now = clock64();                                        \
             atomicAdd(&g_phase_cycles[slot], (unsigned long long)(pt_now - pt_prev));  \
+            if ((chunk) >= kTraceFirst && (chunk) < kTraceFirst + 8)                   \
+                g_phase_trace[slot][(chunk) - kTraceFirst] = pt_now;                   \
             pt_prev = pt_now;                                                          \
         }                                                                              \
     } while (0)
 #else
 #define PT_DECL
-#define PT(slot, cond) do { } while (0)
+#define PT(slot, cond, chunk) do { } while (0)
 #endif
+
+// ---- ablation switches (timing experiments only; results are wrong when any bit is set) ----
+// scripts/ablate.py builds one library per bit and times configs[1] with each phase's work removed while the
+// synchronisation skeleton stays intact: the drop in ms/step is that phase's share of the critical cycle.
+#ifndef GDKVM_ABLATE
+#define GDKVM_ABLATE 0
+#endif
+#define ABL(bit) ((GDKVM_ABLATE >> (bit)) & 1)
+// bits: 0 gating  1 solve levels 0-1  2 solve level 2  3 T' conversion  4 W^T  5 S pass  6 Vnb pass  7 readout
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void kbar() { named_bar_sync(1, kKThreads); }
-// second K-group barrier (id 4) for the middle of the 16x16 merge, where warp 7 only arrives: a warp must
-// never arrive twice in one phase of the same barrier, so this cannot share id 1 with the full syncs
-__device__ __forceinline__ void kbar_mid() { named_bar_sync(4, kKThreads); }
-__device__ __forceinline__ void kbar_mid_arrive() { asm volatile("bar.arrive 4, %0;" ::"r"(kKThreads) : "memory"); }
 
 __device__ __forceinline__ uint32_t scale_bf16x2(uint32_t w, float s) {
     const float lo = __uint_as_float(w << 16), hi = __uint_as_float(w & 0xffff0000u);
@@ -158,62 +169,12 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
 
-// c(16x8) += A[0..15][k] * B[k][0..7] over the 16-wide k slices that intersect [kbeg, kend); A, B are
-// row-major fp32 in shared memory (pitches pa, pb), rounded to fp16 on the fly (11 significant bits;
-// every entry is O(1) and the result is rounded to bf16 afterwards -- tests/chunk_numerics_model.py).
-// Entries outside the triangular supports are exact zeros in memory, so partial slices are harmless.
-template <int KS>
-__device__ __forceinline__ void tile_mma_f16(float (&c)[4], const float* A, int pa, const float* B, int pb,
-                                             int kbeg, int kend, int lane) {
-    const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-        const int k0 = ks * 16;
-        if (k0 + 16 > kbeg && k0 < kend) {
-            const float2 a0 = *reinterpret_cast<const float2*>(A + g * pa + k0 + 2 * t);
-            const float2 a1 = *reinterpret_cast<const float2*>(A + (g + 8) * pa + k0 + 2 * t);
-            const float2 a2 = *reinterpret_cast<const float2*>(A + g * pa + k0 + 2 * t + 8);
-            const float2 a3 = *reinterpret_cast<const float2*>(A + (g + 8) * pa + k0 + 2 * t + 8);
-            const uint32_t af[4] = {pack_f16(a0.x, a0.y), pack_f16(a1.x, a1.y), pack_f16(a2.x, a2.y), pack_f16(a3.x, a3.y)};
-            const float* Bk = B + (k0 + 2 * t) * pb + g;
-            mma_f16(c, af, pack_f16(Bk[0], Bk[pb]), pack_f16(Bk[8 * pb], Bk[9 * pb]));
-        }
-    }
-}
-
-// X21 <- -X22 (L21 X11) for NP independent pairs of adjacent N x N diagonal blocks of the unit
-// lower-triangular matrix held in sA (in place; sY is scratch).  Called by the whole K group.
-// With LAZY7, warp 7 (which has no tile) only arrives at the middle barrier: it runs the gate scan of
-// the next chunk across both stages.
-template <int N, int NP, bool LAZY7>
-__device__ __forceinline__ void tri_merge(float* sA, float* sY, int warp, int lane) {
-    constexpr int NT = N / 8, TPP = (N / 16) * NT, TILES = NP * TPP;
-    const int g = lane >> 2, t = lane & 3;
-    const int pair = warp / TPP, tile = warp % TPP, mt = tile / NT, nt = tile % NT;
-    const int o1 = pair * 2 * N, o2 = o1 + N;
-    float* Y = sY + pair * (N * kPitchY);
-    if (warp < TILES) {      // Y = L21 X11   (X11 lower triangular: rows k < 8 nt contribute nothing)
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        tile_mma_f16<N / 16>(c, sA + (o2 + mt * 16) * kPitchA + o1, kPitchA, sA + o1 * kPitchA + o1 + nt * 8, kPitchA, nt * 8, N, lane);
-        *reinterpret_cast<float2*>(Y + (mt * 16 + g) * kPitchY + nt * 8 + 2 * t) = make_float2(c[0], c[1]);
-        *reinterpret_cast<float2*>(Y + (mt * 16 + g + 8) * kPitchY + nt * 8 + 2 * t) = make_float2(c[2], c[3]);
-    }
-    if (LAZY7) { if (warp != 7) kbar_mid(); } else kbar();
-    if (warp < TILES) {      // X21 = -X22 Y  (X22 lower triangular: columns k > row contribute nothing)
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        tile_mma_f16<N / 16>(c, sA + (o2 + mt * 16) * kPitchA + o2, kPitchA, Y + nt * 8, kPitchY, 0, mt * 16 + 16, lane);
-        float* X21 = sA + (o2 + mt * 16) * kPitchA + o1 + nt * 8 + 2 * t;
-        *reinterpret_cast<float2*>(X21 + g * kPitchA) = make_float2(-c[0], -c[1]);
-        *reinterpret_cast<float2*>(X21 + (g + 8) * kPitchA) = make_float2(-c[2], -c[3]);
-    }
-    kbar();
-}
-
-// Gate scan of one chunk (one warp): Gamma = cumsum(g), decay factors, fast/slow decision.
-__device__ __forceinline__ void gate_scan(const float* gS, const float* btS, float* sGam, float* sE, float* sCj,
-                                          float* sKd, float* sFast, float* ofac, float* post, float* pre,
+// Gate scan of one chunk (one warp; lane l holds g, beta of tokens 2l, 2l+1): Gamma = cumsum(g), decay
+// factors, fast/slow decision.
+__device__ __forceinline__ void gate_scan(const float (&gv)[2], const float (&bv)[2], float* sBt, float* sGam, float* sE,
+                                          float* sCj, float* sKd, float* sFast, float* ofac, float* post, float* pre,
                                           float scale, int lane) {
-    const float g0 = gS[2 * lane], g1 = gS[2 * lane + 1];
+    const float g0 = gv[0], g1 = gv[1];
     float s = g0 + g1;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -224,14 +185,13 @@ __device__ __forceinline__ void gate_scan(const float* gS, const float* btS, flo
     const float Gl = __shfl_sync(0xffffffffu, s, 31);
     const bool fast = Gl > -60.f;
     const float gam = __expf(Gl), e0 = __expf(G0), e1 = __expf(G1);
-    sGam[2 * lane] = G0; sGam[2 * lane + 1] = G1;
-    sE[2 * lane] = e0; sE[2 * lane + 1] = e1;
-    sCj[2 * lane] = btS[2 * lane] * (fast ? __expf(-G0) : 1.f);          // column factor of T'
-    sCj[2 * lane + 1] = btS[2 * lane + 1] * (fast ? __expf(-G1) : 1.f);
-    sKd[2 * lane] = __expf(Gl - G0);                                      // slow path: row factor of K'
-    sKd[2 * lane + 1] = __expf(Gl - G1);
-    ofac[2 * lane] = fast ? scale * e0 : 1.f;                             // readout row factor
-    ofac[2 * lane + 1] = fast ? scale * e1 : 1.f;
+    *reinterpret_cast<float2*>(sBt + 2 * lane) = make_float2(bv[0], bv[1]);
+    *reinterpret_cast<float2*>(sGam + 2 * lane) = make_float2(G0, G1);
+    *reinterpret_cast<float2*>(sE + 2 * lane) = make_float2(e0, e1);
+    *reinterpret_cast<float2*>(sCj + 2 * lane) =                               // column factor of T'
+        make_float2(bv[0] * (fast ? __expf(-G0) : 1.f), bv[1] * (fast ? __expf(-G1) : 1.f));
+    *reinterpret_cast<float2*>(sKd + 2 * lane) = make_float2(__expf(Gl - G0), __expf(Gl - G1));   // slow path: K' factor
+    *reinterpret_cast<float2*>(ofac + 2 * lane) = make_float2(fast ? scale * e0 : 1.f, fast ? scale * e1 : 1.f);   // readout row factor
     if (lane == 0) { *post = fast ? gam : 1.f; *pre = fast ? 1.f : gam; *sFast = fast ? 1.f : 0.f; }
 }
 
@@ -246,7 +206,7 @@ __device__ __forceinline__ void w_unit_mma(uint32_t aK, uint32_t aT, uint8_t* wt
     for (int a = 0; a < 4; ++a)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
-#pragma unroll 1
+#pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
         if (ks * 16 <= ng * 32 + 31) {
             uint32_t af[4], bf0[4], bf1[4];
@@ -275,14 +235,15 @@ __device__ __forceinline__ void w_unit_mma(uint32_t aK, uint32_t aT, uint8_t* wt
     }
 }
 
-// four 128x64x16 tcgen05 MMAs covering K = 64; descriptors advance by a fixed step per K slice
+// four 128x64x16 tcgen05 MMAs covering K = 64; descriptors advance by a fixed step per K slice.
+// Warp-uniform: called by every lane of the (converged) issuer warp, one elected lane issues.
 __device__ __forceinline__ void umma4_ss(uint32_t d, uint64_t a, uint32_t astep, uint64_t bdesc, uint32_t bstep, uint32_t idesc, bool acc0) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_ss(d, a + (uint64_t)(k * astep), bdesc + (uint64_t)(k * bstep), idesc, acc0 || k > 0);
+    for (int k = 0; k < 4; ++k) umma_ss_w(d, a + (uint64_t)(k * astep), bdesc + (uint64_t)(k * bstep), idesc, acc0 || k > 0);
 }
 __device__ __forceinline__ void umma4_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t bstep, uint32_t idesc, bool acc0) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) umma_ts(d, a_tmem + k * 8, bdesc + (uint64_t)(k * bstep), idesc, acc0 || k > 0);
+    for (int k = 0; k < 4; ++k) umma_ts_w(d, a_tmem + k * 8, bdesc + (uint64_t)(k * bstep), idesc, acc0 || k > 0);
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -294,18 +255,15 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     // demote every access below from LDS/STS to generic LD/ST)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
-    float* sA = reinterpret_cast<float*>(smem + kOffA);
-    float* sY = reinterpret_cast<float*>(smem + kOffY);
-    float* sG = reinterpret_cast<float*>(smem + kOffF);   // [2][64] log gates of the chunk in each stage
-    float* sBt = sG + 128;                                // [2][64] beta
+    float* sBt = reinterpret_cast<float*>(smem + kOffF);  // [2][64] beta
     float* sGam = sBt + 128;                              // [2][64] Gamma_i (inclusive cumsum of g)
     float* sE = sGam + 128;                               // [4][64] exp(Gamma_i) of chunk n in slot n & 3
     float* sCj = sE + 256;                                // [2][64] column factor of T': f_j beta_j (fast) | beta_j (slow)
-    float* sKd = sCj + 128;                               // [2][64] row factor of K':    gamma (fast) | exp(Gamma_last - Gamma_i) (slow)
-    float* sOfac = sKd + 128;                             // [4][64] readout row factor of chunk n in slot n & 3: scale e_i | 1
+    float* sKd = sCj + 128;                               // [4][64] slow path: column factor of the second Vnb copy, exp(Gamma_last - Gamma_j)
+    float* sOfac = sKd + 256;                             // [4][64] readout row factor of chunk n in slot n & 3: scale e_i | 1
     float* sPost = sOfac + 256;                           // [4] factor applied to S AFTER chunk n's accumulate: gamma | 1
     float* sPre = sPost + 4;                              // [4] factor applied to S BEFORE chunk n's accumulate: 1 | gamma
-    float* sFast = sPre + 4;                              // [2]
+    float* sFast = sPre + 4;                              // [4] chunk n in slot n & 3
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
 
@@ -316,13 +274,12 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     const float scale = p.scale;
 
     if (tid == 0) {
-        mbar_init(&bars[kTmaFull], 1); mbar_init(&bars[kTmaFull + 1], 1);
+        for (int i = 0; i < 3; ++i) mbar_init(&bars[kKqTile + i], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&bars[kVTile + i], 1);
         mbar_init(&bars[kKqFull], 1); mbar_init(&bars[kKqFree], kKThreads);
         mbar_init(&bars[kTpReady], 1); mbar_init(&bars[kTpReady + 1], 1);
         mbar_init(&bars[kKsideFull], 128 * NH); mbar_init(&bars[kKsideFull + 1], 128 * NH);
         mbar_init(&bars[kKsideEmpty], 1); mbar_init(&bars[kKsideEmpty + 1], 1);
-        mbar_init(&bars[kD1Done], 1);
-        mbar_init(&bars[kKpFull], 1); mbar_init(&bars[kKpFull + 1], 1);
         for (int hh = 0; hh < 2; ++hh) {
             mbar_init(&bars[kSbReady + hh], 128); mbar_init(&bars[kVnFull + hh], 1);
             mbar_init(&bars[kVnbReady + hh], 128); mbar_init(&bars[kSReady + hh], 1);
@@ -350,142 +307,150 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         // =========================================================================================
         const int wq = warp & 3, wh = warp >> 2;
         const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
+        uint8_t* sH = smem + kOffH;
+        const uint32_t aH = sbase + kOffH;
+        // warp 7 owns the gates: it holds g, beta of the NEXT chunk in registers (loaded one chunk period
+        // before they are scanned, so the global-load latency never stalls the group) and scans them while
+        // warps 0-3 run the triangular solve.  Lane l: tokens 2l, 2l+1 of the chunk.
         const int64_t g_off = (int64_t)b * p.g_stride[0] + (int64_t)h * p.g_stride[2];
         const int64_t bt_off = (int64_t)b * p.beta_stride[0] + (int64_t)h * p.beta_stride[2];
-        auto load_gates = [&](int n, float& gv, float& bv) {   // tid < 64: g, beta of row tid of chunk n
-            const int f = n / cpf, c = ((n - f * cpf) << 6) + tid;
-            gv = 0.f; bv = 0.f;                                  // pad rows: exact no-ops
-            if (c < C) {
-                const int64_t t = (int64_t)f * C + c;
-                gv = load_gate(p.g, g_off + t * p.g_stride[1], p.gate_dtype);
-                bv = load_gate(p.beta, bt_off + t * p.beta_stride[1], p.gate_dtype);
+        auto load_gates = [&](int n, float (&gv)[2], float (&bv)[2]) {
+            const int f = n / cpf;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = ((n - f * cpf) << 6) + 2 * lane + e;
+                gv[e] = 0.f; bv[e] = 0.f;                        // pad rows: exact no-ops
+                if (c < C) {
+                    const int64_t t = (int64_t)f * C + c;
+                    gv[e] = load_gate(p.g, g_off + t * p.g_stride[1], p.gate_dtype);
+                    bv[e] = load_gate(p.beta, bt_off + t * p.beta_stride[1], p.gate_dtype);
+                }
             }
         };
-        if (tid < 64) { float gv, bv; load_gates(0, gv, bv); sG[tid] = gv; sBt[tid] = bv; }
-        kbar();
-        if (warp == 7) gate_scan(sG, sBt, sGam, sE, sCj, sKd, sFast, sOfac, sPost, sPre, scale, lane);   // chunk 0 -> slot 0
+        auto scan_chunk = [&](int m, const float (&gv)[2], const float (&bv)[2]) {
+            gate_scan(gv, bv, sBt + (m & 1) * 64, sGam + (m & 1) * 64, sE + (m & 3) * 64, sCj + (m & 1) * 64, sKd + (m & 3) * 64,
+                      sFast + (m & 3), sOfac + (m & 3) * 64, sPost + (m & 3), sPre + (m & 3), scale, lane);
+        };
+        float g_nx[2] = {0.f, 0.f}, b_nx[2] = {0.f, 0.f};
+        if (warp == 7) {
+            load_gates(0, g_nx, b_nx);
+            scan_chunk(0, g_nx, b_nx);
+            if (NC > 1) load_gates(1, g_nx, b_nx);
+        }
         kbar();
 
         PT_DECL
         for (int n = 0; n < NC; ++n) {
             const int st = n & 1;
-            uint8_t* sp = smem + st * kStageBytes;
+            uint8_t* sp = smem + kOffKq + (uint32_t)(n % 3) * kKqSlotBytes;   // K | Q tiles of chunk n
             const float* btS = sBt + st * 64;
-            const float* eS = sE + (n & 3) * 64;
-            float g_next = 0.f, b_next = 0.f;
-            if (n + 1 < NC && tid < 64) load_gates(n + 1, g_next, b_next);
             // operand buffers of this stage are free once every MMA of chunk n-2 has completed
-            if (n >= 2) mbar_wait(&bars[kKsideEmpty + st], (uint32_t)((n >> 1) - 1) & 1u);
-            const bool fast = sFast[st] != 0.f;
+            if (n >= 2) mbar_wait_inl(&bars[kKsideEmpty + st], (uint32_t)((n >> 1) - 1) & 1u);
+            const bool fast = sFast[n & 3] != 0.f;
 
-            // [K;Q]K^T accumulators -> masked A (fp32 solve matrix) and P (bf16 operand), row factors only
-            mbar_wait(&bars[kTmaFull + st], (uint32_t)(n >> 1) & 1u);   // tiles visible to this thread's loads
-            mbar_wait(&bars[kKqFull], (uint32_t)n & 1u);
+            // [K;Q]K^T accumulators -> masked A (fp16 solve matrix H) and P (bf16 operand)
+            mbar_wait_inl(&bars[kKqTile + n % 3], (uint32_t)(n / 3) & 1u);   // tiles visible to this thread's loads
+            mbar_wait_inl(&bars[kKqFull], (uint32_t)n & 1u);
             tc_fence_after_sync();
-            PT(0, tid == 0);   // waits: buffers free, tiles landed, [K;Q]K^T done
-#pragma unroll 1
-            for (int c8 = 0; c8 < 4; ++c8) {      // 8 accumulator columns per step keeps the loop body in the L0 i-cache
-                uint32_t r[8];
-                tmem_ld8(lane_addr + kColKQ + wh * 32 + c8 * 8, r);
+            PT(0, tid == 0, n);   // waits: buffers free, tiles landed, [K;Q]K^T done
+            if (!ABL(0)) {
+                uint32_t r[32], pk[16];
+                tmem_ld32(lane_addr + kColKQ + wh * 32, r);
                 tmem_wait_ld();
-                const int j0 = wh * 32 + c8 * 8;
+                const int j0 = wh * 32;
+                const float* Gm = sGam + st * 64;
+                if (!fast) {           // rare: per-element decay exp(Gamma_i - Gamma_j) (and the readout scale) applied first
+                    const int i = (wq & 1) * 32 + lane;
+                    const float gi = Gm[i], sc = wq < 2 ? 1.f : scale;
+#pragma unroll 1
+                    for (int jj = 0; jj < 32; jj += 4) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float d = sc * __expf(fminf(gi - Gm[j0 + jj + e], 0.f));
+                            // r[] must stay in registers: compile-time indices only
+                            switch (jj) {
+                                case 0: r[e] = __float_as_uint(__uint_as_float(r[e]) * d); break;
+                                case 4: r[4 + e] = __float_as_uint(__uint_as_float(r[4 + e]) * d); break;
+                                case 8: r[8 + e] = __float_as_uint(__uint_as_float(r[8 + e]) * d); break;
+                                case 12: r[12 + e] = __float_as_uint(__uint_as_float(r[12 + e]) * d); break;
+                                case 16: r[16 + e] = __float_as_uint(__uint_as_float(r[16 + e]) * d); break;
+                                case 20: r[20 + e] = __float_as_uint(__uint_as_float(r[20 + e]) * d); break;
+                                case 24: r[24 + e] = __float_as_uint(__uint_as_float(r[24 + e]) * d); break;
+                                default: r[28 + e] = __float_as_uint(__uint_as_float(r[28 + e]) * d); break;
+                            }
+                        }
+                    }
+                }
                 if (wq < 2) {          // rows of K K^T:  A_ij = beta_i (k_i.k_j),  j < i
                     const int i = wq * 32 + lane;
                     const float bi = btS[i];
-                    float o[8];
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) o[jj] = (j0 + jj) < i ? __uint_as_float(r[jj]) * bi : 0.f;
-                    *reinterpret_cast<float4*>(sA + i * kPitchA + j0) = make_float4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<float4*>(sA + i * kPitchA + j0 + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                } else {               // rows of Q K^T:  P_ij = (q_i.k_j),  j <= i   (scale e_i is applied in the readout)
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const int j = j0 + 2 * jj;
+                        pk[jj] = tri::pack_f16(j < i ? __uint_as_float(r[2 * jj]) * bi : 0.f, j + 1 < i ? __uint_as_float(r[2 * jj + 1]) * bi : 0.f);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(sH + sw128_offset(i, wh * 4 + c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                } else {               // rows of Q K^T:  P_ij = (q_i.k_j),  j <= i   (fast: scale e_i is applied in the readout)
                     const int i = (wq - 2) * 32 + lane;
-                    const float sce = fast ? 1.f : scale;
-                    float o[8];
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) o[jj] = (j0 + jj) <= i ? __uint_as_float(r[jj]) * sce : 0.f;
-                    *reinterpret_cast<uint4*>(smem + kOffPp + st * 8192 + sw128_offset(i, wh * 4 + c8)) =
-                        make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]), pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+                    for (int jj = 0; jj < 16; ++jj) {
+                        const int j = j0 + 2 * jj;
+                        pk[jj] = pack_bf16(j <= i ? __uint_as_float(r[2 * jj]) : 0.f, j + 1 <= i ? __uint_as_float(r[2 * jj + 1]) : 0.f);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(smem + kOffPp + st * 8192 + sw128_offset(i, wh * 4 + c)) =
+                            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                 }
             }
             tc_fence_before_sync();
             mbar_arrive(&bars[kKqFree]);
-            PT(1, tid == 0);   // gating (own work)
-            kbar();
-            PT(2, tid == 0);   // gating (barrier wait)
-            if (!fast) {   // rare: chunk decay below e^-60 -> per-element exp(Gamma_i - Gamma_j) instead of folded factors
-                const float* Gm = sGam + st * 64;
+            if (!fast) {   // rare: chunk decay below e^-60.  Q~ = scale e_i Q in place (the swizzle keeps rows intact);
+                           // K' = K exp(Gamma_last - Gamma_i) is folded into a second Vnb copy by the state warps
+                const float* eS = sE + (n & 3) * 64;
 #pragma unroll 1
-                for (int idx = tid; idx < 4096; idx += kKThreads) {
-                    const int i = idx >> 6, j = idx & 63;
-                    if (j < i) sA[i * kPitchA + j] *= __expf(Gm[i] - Gm[j]);
+                for (int idx = tid; idx < 512; idx += kKThreads) {
+                    uint4* pq = reinterpret_cast<uint4*>(sp + 8192 + (idx << 4));
+                    *pq = scale_row8(*pq, scale * eS[idx >> 3]);
                 }
-#pragma unroll 1
-                for (int idx = tid; idx < 2048; idx += kKThreads) {
-                    const int i = idx >> 5, j = (idx & 31) * 2;
-                    uint32_t* w = reinterpret_cast<uint32_t*>(smem + kOffPp + st * 8192 + sw128_offset(i, j >> 3) + (j & 7) * 2);
-                    const uint32_t v = *w;
-                    *w = pack_bf16(__uint_as_float(v << 16) * __expf(fminf(Gm[i] - Gm[j], 0.f)),
-                                   __uint_as_float(v & 0xffff0000u) * __expf(fminf(Gm[i] - Gm[j + 1], 0.f)));
-                }
-                mbar_wait(&bars[kKpFull + st], (uint32_t)(n >> 1) & 1u);
-                const float* kdS = sKd + st * 64;
-#pragma unroll 1
-                for (int idx = tid; idx < 512; idx += kKThreads) {   // (row, 16B chunk): the swizzle keeps rows intact
-                    const int row = idx >> 3, off = idx << 4;
-                    uint4* pk = reinterpret_cast<uint4*>(smem + kOffKp + st * 8192 + off);
-                    uint4* pq = reinterpret_cast<uint4*>(sp + kOffQt + off);
-                    *pk = scale_row8(*pk, kdS[row]);                 // K' = K exp(Gamma_last - Gamma_i)
-                    *pq = scale_row8(*pq, scale * eS[row]);          // Q~ = scale e_i Q
-                }
-                kbar();
             }
+            PT(1, tid == 0, n);   // gating (own work)
+            kbar();
+            PT(2, tid == 0, n);   // gating (barrier wait)
 
-            // 16x16 diagonal blocks by forward substitution (warps 0-1)
-            if (warp < 2) {
-                const int blk = tid >> 4, c = tid & 15;
-                float* Ab = sA + (blk * 16) * kPitchA + blk * 16;
-                float x[16], acc[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    x[j] = (j == c) ? 1.f : -acc[j];
-#pragma unroll
-                    for (int i = j + 1; i < 16; ++i) acc[i] = fmaf(Ab[i * kPitchA + j], x[j], acc[i]);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) Ab[i * kPitchA + c] = x[i];
-                if (n + 1 < NC) { sG[(st ^ 1) * 64 + tid] = g_next; sBt[(st ^ 1) * 64 + tid] = b_next; }
+            // (I + A)^-1 in place: levels 0-1 on warps 0-1, level 2 on warps 0-3; warp 7 scans the gates of chunk n+1
+            if (warp < 2 && !ABL(1)) tri::solve_levels01(sH, aH, warp, lane);
+            PT(3, tid == 0, n);   // diagonal blocks + level 1
+            if (warp < 4) {
+                named_bar_sync(5, 128);
+                if (!ABL(2)) tri::solve_level2(aH, warp, lane, 5); else named_bar_sync(5, 128);
+            } else if (warp == 7 && n + 1 < NC) {
+                scan_chunk(n + 1, g_nx, b_nx);
+                if (n + 2 < NC) load_gates(n + 2, g_nx, b_nx);
             }
-            PT(3, tid == 0);   // diagonal 16x16 inverses (own work)
+            PT(4, tid == 0, n);   // level 2
             kbar();
-            // block merges; warp 7 has no 16x16 merge tile and scans the gates of chunk n+1 meanwhile
-            if (warp == 7) kbar_mid_arrive();    // middle barrier of the 16x16 merge: warp 7 is not waited for
-            if (warp == 7 && n + 1 < NC)
-                gate_scan(sG + (st ^ 1) * 64, sBt + (st ^ 1) * 64, sGam + (st ^ 1) * 64, sE + ((n + 1) & 3) * 64, sCj + (st ^ 1) * 64,
-                          sKd + (st ^ 1) * 64, sFast + (st ^ 1), sOfac + ((n + 1) & 3) * 64, sPost + ((n + 1) & 3), sPre + ((n + 1) & 3),
-                          scale, lane);
-            tri_merge<16, 2, true>(sA, sY, warp, lane);
-            PT(4, tid == 0);   // 16x16 merges
-            tri_merge<32, 1, false>(sA, sY, warp, lane);
-            PT(5, tid == 0);   // 32x32 merge
-            {   // T' = X diag(c) -> bf16, K-major swizzled rows (thread: 4 consecutive columns of one row, 4 tasks)
+            PT(5, tid == 0, n);   // solve barrier
+            {   // T' = X diag(c) -> bf16, K-major swizzled rows: H and T' share one layout (thread: one 16-byte chunk, 2 tasks)
                 const float* cjS = sCj + st * 64;
-#pragma unroll 1
-                for (int it = 0; it < 4; ++it) {
-                    const int task = it * kKThreads + tid, i = task >> 4, q4 = task & 15;
-                    const float4 x = *reinterpret_cast<const float4*>(sA + i * kPitchA + q4 * 4);
-                    const float4 cj = *reinterpret_cast<const float4*>(cjS + q4 * 4);
-                    *reinterpret_cast<uint2*>(smem + kOffTp + st * 8192 + sw128_offset(i, q4 >> 1) + (q4 & 1) * 8) =
-                        make_uint2(pack_bf16(x.x * cj.x, x.y * cj.y), pack_bf16(x.z * cj.z, x.w * cj.w));
+#pragma unroll
+                for (int it = 0; it < (ABL(3) ? 0 : 2); ++it) {
+                    const int task = it * kKThreads + tid, i = task >> 3, c = task & 7;
+                    const uint32_t off = sw128_offset(i, c);
+                    const uint4 hx = *reinterpret_cast<const uint4*>(sH + off);
+                    const float4 c0 = *reinterpret_cast<const float4*>(cjS + c * 8), c1 = *reinterpret_cast<const float4*>(cjS + c * 8 + 4);
+                    const float2 x0 = tri::unpack_f16(hx.x), x1 = tri::unpack_f16(hx.y), x2 = tri::unpack_f16(hx.z), x3 = tri::unpack_f16(hx.w);
+                    *reinterpret_cast<uint4*>(smem + kOffTp + st * 8192 + off) =
+                        make_uint4(pack_bf16(x0.x * c0.x, x0.y * c0.y), pack_bf16(x1.x * c0.z, x1.y * c0.w),
+                                   pack_bf16(x2.x * c1.x, x2.y * c1.y), pack_bf16(x3.x * c1.z, x3.y * c1.w));
                 }
             }
             fence_proxy_async_smem();
             kbar();
-            PT(6, tid == 0);   // T' conversion
+            PT(6, tid == 0, n);   // T' conversion
             if (tid == 0) mbar_arrive(&bars[kTpReady + st]);
-
         }
     } else if (warp < 16) {
         // =========================================================================================
@@ -514,14 +479,14 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             auto readout = [&](int m) {
                 mbar_wait(&bars[kOFull + hh], (uint32_t)m & 1u);
                 tc_fence_after_sync();
-                PT(23, tid == 256);   // wait: readout accumulators (after Vnb -> state update + intra-chunk MMAs)
+                PT(23, tid == 256, m);   // wait: readout accumulators (after Vnb -> state update + intra-chunk MMAs)
                 if (stid == 0) tma_store_wait_read0();      // previous readout has left the staging buffer
                 named_bar_sync(bar_id, 128);
-                PT(24, tid == 256);   // wait: staging buffer free + group barrier
+                PT(24, tid == 256, m);   // wait: staging buffer free + group barrier
                 const float* of = sOfac + (m & 3) * 64 + 2 * (lane & 3);
                 const uint32_t ost_half = sbase + kOffOst + hh * 16384;
 #pragma unroll
-                for (int grp = 0; grp < 2; ++grp) {
+                for (int grp = 0; grp < (ABL(7) ? 0 : 2); ++grp) {
                     uint32_t r[32];
                     tmem_ld_16x256b_x8(tmem + ((uint32_t)(wq * 32 + grp * 16) << 16) + kColO + hh * 64, r);
                     tmem_wait_ld();
@@ -551,29 +516,33 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                     tma_store_commit();
                 }
             };
+            // W^T of chunk m: 8 units of 16 key dims x 32 tokens shared by the state warps (needs the K side of chunk m)
+            auto wt_operand = [&](int m) {
+                const int st = m & 1;
+                mbar_wait(&bars[kTpReady + st], (uint32_t)(m >> 1) & 1u);          // K side of chunk m published
+                PT(16, tid == 256, m);   // wait: K side of chunk m
+                const int sw = (warp - 8);                                          // 0 .. 4 NH - 1
+                for (int u = sw; u < (ABL(4) ? 0 : 8); u += 4 * NH)
+                    w_unit_mma(sbase + kOffKq + (uint32_t)(m % 3) * kKqSlotBytes, sbase + kOffTp + st * 8192, smem + kOffWt + st * 8192,
+                               sE + (m & 3) * 64, u & 3, u >> 2, lane);
+                fence_proxy_async_smem();
+                mbar_arrive(&bars[kKsideFull + st]);
+                PT(22, tid == 256, m);   // W^T mma.sync
+            };
+            // Order inside one chunk: only the S pass and the Vnb pass sit between the state-side MMAs of the
+            // recurrence; the readout of chunk n-1 runs under the Vn correction MMA and the W^T operand of chunk
+            // n+1 under the state update MMA.
+            wt_operand(0);
             for (int n = 0; n < NC; ++n) {
                 const int st = n & 1;
-                if (n >= 1) readout(n - 1);                                         // while the K side of chunk n finishes
-                PT(19, tid == 256);   // readout of chunk n-1
-                mbar_wait(&bars[kTpReady + st], (uint32_t)(n >> 1) & 1u);          // K side of chunk n published
-                PT(16, tid == 256);   // wait: K side of chunk n
-                {   // W^T of chunk n: 8 units of 16 key dims x 32 tokens shared by the state warps
-                    const int sw = (warp - 8);                                      // 0 .. 4 NH - 1
-                    for (int u = sw; u < 8; u += 4 * NH)
-                        w_unit_mma(sbase + st * kStageBytes + kOffKt, sbase + kOffTp + st * 8192, smem + kOffWt + st * 8192,
-                                   sE + (n & 3) * 64, u & 3, u >> 2, lane);
-                    fence_proxy_async_smem();
-                    mbar_arrive(&bars[kKsideFull + st]);
-                }
-                PT(22, tid == 256);   // W^T mma.sync
                 if (n >= 1) mbar_wait(&bars[kSReady + hh], (uint32_t)(n - 1) & 1u);
                 tc_fence_after_sync();
-                PT(17, tid == 256);   // wait: state update of chunk n-1
+                PT(17, tid == 256, n);   // wait: state update of chunk n-1
                 {   // S_n = post_{n-1} * accumulator;  Sb = bf16(S_n) (operand copy);  accumulator <- pre_n * S_n
                     const float post = n >= 1 ? sPost[(n - 1) & 3] : 1.f, pre = sPre[n & 3];
                     const bool rescale = pre != 1.f || post != 1.f;
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
+                    for (int half = 0; half < (ABL(5) ? 0 : 2); ++half) {
                         uint32_t r[32], pk[16];
                         tmem_ld32(lane_addr + kColS + hh * 64 + half * 32, r);
                         tmem_wait_ld();
@@ -592,11 +561,19 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 }
                 tc_fence_before_sync();
                 mbar_arrive(&bars[kSbReady + hh]);
-                PT(18, tid == 256);   // S pass
+                PT(18, tid == 256, n);   // S pass
+                if (n >= 1) readout(n - 1);
+                PT(19, tid == 256, n - 1);   // readout of chunk n-1
                 mbar_wait(&bars[kVnFull + hh], (uint32_t)n & 1u);
                 tc_fence_after_sync();
-                PT(20, tid == 256);   // wait: Vn
-                {   // Vnb = bf16(Vn^T) written over the first half of Vn (TMEM A-operand); both fp32 halves are
+                PT(20, tid == 256, n);   // wait: Vn
+                if (stid == 0 && n + 2 < NC) {   // U of chunk n is complete: its V half-tile slot takes chunk n + 2
+                    const int m = n + 2, f = m / cpf, c0 = (m - f * cpf) << 6;
+                    uint64_t* vb = &bars[kVTile + st * 2 + hh];
+                    mbar_arrive_expect_tx(vb, 16384u);
+                    tma_load_5d(smem + kOffV + st * kVSlotBytes + hh * 16384, &mv, vb, 0, c0, h * VB + hh * 2, f, b);
+                }
+                if (!ABL(6)) {   // Vnb = bf16(Vn^T) written over the first half of Vn (TMEM A-operand); both fp32 halves are
                     // in registers before the bf16 columns overwrite them
                     uint32_t r0[32], r1[32], pk[32];
                     tmem_ld32(lane_addr + kColVn + hh * 64, r0);
@@ -608,11 +585,21 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                         pk[16 + j] = pack_bf16(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
                     }
                     tmem_st32(lane_addr + kColVn + hh * 64, pk);
+                    if (sFast[n & 3] == 0.f) {   // rare: second copy Vnb diag(exp(Gamma_last - Gamma_j)) for the state update
+                        const float* kd = sKd + (n & 3) * 64;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            pk[j] = pack_bf16(__uint_as_float(r0[2 * j]) * kd[2 * j], __uint_as_float(r0[2 * j + 1]) * kd[2 * j + 1]);
+                            pk[16 + j] = pack_bf16(__uint_as_float(r1[2 * j]) * kd[32 + 2 * j], __uint_as_float(r1[2 * j + 1]) * kd[33 + 2 * j]);
+                        }
+                        tmem_st32(lane_addr + kColVn + hh * 64 + 32, pk);
+                    }
                     tmem_wait_st();
                 }
                 tc_fence_before_sync();
                 mbar_arrive(&bars[kVnbReady + hh]);
-                PT(21, tid == 256);   // Vnb pass
+                PT(21, tid == 256, n);   // Vnb pass
+                if (n + 1 < NC) wt_operand(n + 1);
             }
             readout(NC - 1);
             mbar_wait(&bars[kSReady + hh], (uint32_t)(NC - 1) & 1u);
@@ -636,87 +623,95 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         // =========================================================================================
         // issuer K: TMA loads (one chunk of prefetch) + the [K;Q]K^T MMA
         // =========================================================================================
-        if (lane == 0) {
-            const uint32_t stage_tx = 16384u + (uint32_t)VB * 8192u;
-            auto issue_loads = [&](int n) {
-                const int st = n & 1, f = n / cpf, c0 = (n - f * cpf) << 6;
-                uint8_t* sp = smem + st * kStageBytes;
-                mbar_arrive_expect_tx(&bars[kTmaFull + st], stage_tx);
-                tma_load_5d(sp + kOffKt, &mk, &bars[kTmaFull + st], 0, c0, f, h, b);
-                tma_load_5d(sp + kOffQt, &mq, &bars[kTmaFull + st], 0, c0, f, h, b);
-                tma_load_5d(sp + kOffVt, &mv, &bars[kTmaFull + st], 0, c0, h * VB, f, b);
+        {
+            auto issue_kq = [&](int m) {         // one elected lane arms the barrier and issues the K and Q tile loads
+                const int slot = m % 3, f = m / cpf, c0 = (m - f * cpf) << 6;
+                uint8_t* sp = smem + kOffKq + (uint32_t)slot * kKqSlotBytes;
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&bars[kKqTile + slot], 16384u);
+                    tma_load_5d(sp, &mk, &bars[kKqTile + slot], 0, c0, f, h, b);
+                    tma_load_5d(sp + 8192, &mq, &bars[kKqTile + slot], 0, c0, f, h, b);
+                }
+                __syncwarp();
             };
-            issue_loads(0);
+            for (int m = 0; m < 2 && m < NC; ++m) {      // prologue: chunks 0 and 1 (their V tiles too)
+                issue_kq(m);
+                if (elect_one()) {
+                    const int f = m / cpf, c0 = (m - f * cpf) << 6;
+                    for (int hh = 0; hh < NH; ++hh) {
+                        uint64_t* vb = &bars[kVTile + m * 2 + hh];
+                        mbar_arrive_expect_tx(vb, 16384u);
+                        tma_load_5d(smem + kOffV + m * kVSlotBytes + hh * 16384, &mv, vb, 0, c0, h * VB + hh * 2, f, b);
+                    }
+                }
+                __syncwarp();
+            }
 #pragma unroll 1
             for (int n = 0; n < NC; ++n) {
-                const int st = n & 1;
-                const uint64_t dK = umma_smem_desc_sw128(sbase + st * kStageBytes + kOffKt, 16, 1024);
-                mbar_wait(&bars[kTmaFull + st], (uint32_t)(n >> 1) & 1u);
-                if (n >= 1) mbar_wait(&bars[kKqFree], (uint32_t)(n - 1) & 1u);      // accumulators of chunk n-1 drained
+                const int slot = n % 3;
+                const uint64_t dK = umma_smem_desc_sw128(sbase + kOffKq + (uint32_t)slot * kKqSlotBytes, 16, 1024);
+                mbar_wait_inl(&bars[kKqTile + slot], (uint32_t)(n / 3) & 1u);
+                if (n >= 1) mbar_wait_inl(&bars[kKqFree], (uint32_t)(n - 1) & 1u);  // accumulators of chunk n-1 drained
                 tc_fence_after_sync();
                 umma4_ss(tmem + kColKQ, dK, 2, dK, 2, kIdKK, false);                // [K;Q] K^T
-                umma_commit(&bars[kKqFull]);
-                if (n + 1 < NC) {                    // refill the other stage: chunk n-1 no longer reads it
-                    if (n >= 1) mbar_wait(&bars[kD1Done], (uint32_t)(n - 1) & 1u);
-                    issue_loads(n + 1);
-                }
-                {   // second copy of the K tile for the state update (raw K; its buffer is free once chunk n-2 completed)
-                    if (n >= 2) mbar_wait(&bars[kKsideEmpty + st], (uint32_t)((n >> 1) - 1) & 1u);
-                    const int f = n / cpf, c0 = (n - f * cpf) << 6;
-                    mbar_arrive_expect_tx(&bars[kKpFull + st], 8192u);
-                    tma_load_5d(smem + kOffKp + st * 8192, &mk, &bars[kKpFull + st], 0, c0, f, h, b);
+                umma_commit_w(&bars[kKqFull]);
+                if (n + 2 < NC) {                    // ring slot of chunk n-1 takes chunk n+2 once every MMA of chunk n-1 completed
+                    if (n >= 1) mbar_wait_inl(&bars[kKsideEmpty + ((n - 1) & 1)], (uint32_t)((n - 1) >> 1) & 1u);
+                    issue_kq(n + 2);
                 }
             }
         }
-        __syncwarp();
     } else {
         // =========================================================================================
         // issuer S: the state-side MMAs
         // =========================================================================================
-        if (lane == 0) {
+        {
             PT_DECL
 #pragma unroll 1
             for (int n = 0; n < NC; ++n) {
                 const int st = n & 1;
-                const uint32_t aQt = sbase + st * kStageBytes + kOffQt, aVt = aQt + 8192;
+                const uint32_t aKt = sbase + kOffKq + (uint32_t)(n % 3) * kKqSlotBytes, aQt = aKt + 8192;
+                const uint32_t aVt = sbase + kOffV + st * kVSlotBytes;
                 const uint64_t dTp = umma_smem_desc_sw128(sbase + kOffTp + st * 8192, 16, 1024);
                 const uint64_t dWt = umma_smem_desc_sw128(sbase + kOffWt + st * 8192, 8192, 1024);
-                const uint64_t dKp = umma_smem_desc_sw128(sbase + kOffKp + st * 8192, 8192, 1024);
+                const uint64_t dKp = umma_smem_desc_sw128(aKt, 8192, 1024);      // raw K tile as the MN-major B of the state update
                 const uint64_t dPp = umma_smem_desc_sw128(sbase + kOffPp + st * 8192, 16, 1024);
                 const uint64_t dQt = umma_smem_desc_sw128(aQt, 16, 1024);
-                mbar_wait(&bars[kTpReady + st], (uint32_t)(n >> 1) & 1u);
+                mbar_wait_inl(&bars[kTpReady + st], (uint32_t)(n >> 1) & 1u);
                 tc_fence_after_sync();
-                PT(32, true);   // issuer S: wait K side
-                for (int hh = 0; hh < NH; ++hh)      // Vn^T[h] = V^T[h] T'^T   (in order after the MMAs of chunk n-1)
+                PT(32, lane == 0, n);   // issuer S: wait K side
+                const uint32_t vn_off = sFast[n & 3] != 0.f ? 0u : 32u;   // slow path: the state update reads the second Vnb copy
+                for (int hh = 0; hh < NH; ++hh) {    // Vn^T[h] = V^T[h] T'^T   (in order after the MMAs of chunk n-1)
+                    mbar_wait_inl(&bars[kVTile + st * 2 + hh], (uint32_t)(n >> 1) & 1u);
+                    tc_fence_after_sync();
                     umma4_ss(tmem + kColVn + hh * 64, umma_smem_desc_sw128(aVt + hh * 16384, 8192, 1024), 128, dTp, 2, kIdMnA, false);
-                mbar_wait(&bars[kKsideFull + st], (uint32_t)(n >> 1) & 1u);
-                PT(33, true);   // issuer S: issue U, wait W^T operand
+                }
+                PT(38, lane == 0, n);   // issuer S: issue U
+                mbar_wait_inl(&bars[kKsideFull + st], (uint32_t)(n >> 1) & 1u);
+                PT(33, lane == 0, n);   // issuer S: issue U, wait W^T operand
                 for (int hh = 0; hh < NH; ++hh) {    // Vn^T[h] -= Sb[h] W^T
-                    mbar_wait(&bars[kSbReady + hh], (uint32_t)n & 1u);
+                    mbar_wait_inl(&bars[kSbReady + hh], (uint32_t)n & 1u);
                     tc_fence_after_sync();
                     umma4_ts(tmem + kColVn + hh * 64, tmem + kColSb + hh * 32, dWt, 128, kIdMnBneg, true);
-                    umma_commit(&bars[kVnFull + hh]);
+                    umma_commit_w(&bars[kVnFull + hh]);
                 }
-                PT(34, true);   // issuer S: wait Sb, issue Vn correction
+                PT(34, lane == 0, n);   // issuer S: wait Sb, issue Vn correction
                 for (int hh = 0; hh < NH; ++hh) {    // O^T[h] = Sb[h] Q~^T
-                    if (n >= 1) mbar_wait(&bars[kOFree + hh], (uint32_t)(n - 1) & 1u);
+                    if (n >= 1) mbar_wait_inl(&bars[kOFree + hh], (uint32_t)(n - 1) & 1u);
                     tc_fence_after_sync();
                     umma4_ts(tmem + kColO + hh * 64, tmem + kColSb + hh * 32, dQt, 2, kIdKK, false);
                 }
-                umma_commit(&bars[kD1Done]);
-                PT(35, true);   // issuer S: wait O free, issue inter-chunk readout
-                mbar_wait(&bars[kKpFull + st], (uint32_t)(n >> 1) & 1u);
-                PT(36, true);   // issuer S: wait K copy
+                PT(35, lane == 0, n);   // issuer S: wait O free, issue inter-chunk readout
                 for (int hh = 0; hh < NH; ++hh) {    // S^T[h] += Vnb[h] K' ;  O^T[h] += Vnb[h] P^T
-                    mbar_wait(&bars[kVnbReady + hh], (uint32_t)n & 1u);
+                    mbar_wait_inl(&bars[kVnbReady + hh], (uint32_t)n & 1u);
                     tc_fence_after_sync();
-                    umma4_ts(tmem + kColS + hh * 64, tmem + kColVn + hh * 64, dKp, 128, kIdMnB, true);
-                    umma_commit(&bars[kSReady + hh]);
+                    umma4_ts(tmem + kColS + hh * 64, tmem + kColVn + hh * 64 + vn_off, dKp, 128, kIdMnB, true);
+                    umma_commit_w(&bars[kSReady + hh]);
                     umma4_ts(tmem + kColO + hh * 64, tmem + kColVn + hh * 64, dPp, 2, kIdKK, true);
-                    umma_commit(&bars[kOFull + hh]);
+                    umma_commit_w(&bars[kOFull + hh]);
                 }
-                umma_commit(&bars[kKsideEmpty + st]);
-                PT(37, true);   // issuer S: wait Vnb, issue state update + intra-chunk readout
+                umma_commit_w(&bars[kKsideEmpty + st]);
+                PT(37, lane == 0, n);   // issuer S: wait Vnb, issue state update + intra-chunk readout
             }
         }
         __syncwarp();
@@ -742,6 +737,13 @@ extern "C" int gdkvm_debug_phase_cycles(unsigned long long* out, int n) {
     for (int i = 0; i < n && i < 64; ++i) out[i] = h[i];
     unsigned long long z[64] = {0};
     cudaMemcpyToSymbol(gdkvm::g_phase_cycles, z, sizeof z);
+    return 0;
+}
+extern "C" int gdkvm_debug_phase_trace(long long* out, int n) {   // out[64][8]
+    long long h[64 * 8];
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(h, gdkvm::g_phase_trace, sizeof h) != cudaSuccess) return -1;
+    for (int i = 0; i < n && i < 64 * 8; ++i) out[i] = h[i];
     return 0;
 }
 namespace gdkvm {
@@ -788,11 +790,11 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
         if (rc == 0) rc = make_tmap(&mk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.k, dims, sk, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc != 0) return (int)cudaErrorInvalidValue;
     }
-    // v: (64 values, token-in-frame, head x value-block, frame, clip), whole V per box;
-    // o: same geometry, one 128-column half per box (each state warpgroup stores its own half)
+    // v, o: (64 values, token-in-frame, head x value-block, frame, clip), one 128-column half per box
+    // (each state warpgroup loads / stores its own half)
     {
         const uint64_t dims[5] = {64, (uint64_t)C, H * (V / 64), (uint64_t)F, B};
-        const uint32_t boxv[5] = {64, 64, (uint32_t)(V / 64), 1, 1};
+        const uint32_t boxv[5] = {64, 64, 2, 1, 1};      // one 128-column value half per box (per-half ring slots)
         const uint32_t boxo[5] = {64, 64, 2, 1, 1};
         const uint64_t sv[4] = {(uint64_t)p.v_stride[1] * 2, 128, (uint64_t)p.v_stride[1] * 2 * C, (uint64_t)p.v_stride[0] * 2};
         const uint64_t so[4] = {(uint64_t)p.o_stride[1] * 2, 128, (uint64_t)p.o_stride[1] * 2 * C, (uint64_t)p.o_stride[0] * 2};
