@@ -567,12 +567,6 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 mbar_wait(&bars[kVnFull + hh], (uint32_t)n & 1u);
                 tc_fence_after_sync();
                 PT(20, tid == 256, n);   // wait: Vn
-                if (stid == 0 && n + 2 < NC) {   // U of chunk n is complete: its V half-tile slot takes chunk n + 2
-                    const int m = n + 2, f = m / cpf, c0 = (m - f * cpf) << 6;
-                    uint64_t* vb = &bars[kVTile + st * 2 + hh];
-                    mbar_arrive_expect_tx(vb, 16384u);
-                    tma_load_5d(smem + kOffV + st * kVSlotBytes + hh * 16384, &mv, vb, 0, c0, h * VB + hh * 2, f, b);
-                }
                 if (!ABL(6)) {   // Vnb = bf16(Vn^T) written over the first half of Vn (TMEM A-operand); both fp32 halves are
                     // in registers before the bf16 columns overwrite them
                     uint32_t r0[32], r1[32], pk[32];
@@ -598,6 +592,12 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 }
                 tc_fence_before_sync();
                 mbar_arrive(&bars[kVnbReady + hh]);
+                if (stid == 0 && n + 2 < NC) {   // U of chunk n is complete: its V half-tile slot takes chunk n + 2
+                    const int m = n + 2, f = m / cpf, c0 = (m - f * cpf) << 6;
+                    uint64_t* vb = &bars[kVTile + st * 2 + hh];
+                    mbar_arrive_expect_tx(vb, 16384u);
+                    tma_load_5d(smem + kOffV + st * kVSlotBytes + hh * 16384, &mv, vb, 0, c0, h * VB + hh * 2, f, b);
+                }
                 PT(21, tid == 256, n);   // Vnb pass
                 if (n + 1 < NC) wt_operand(n + 1);
             }
