@@ -43,13 +43,41 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// -DGDKVM_DEBUG_WAIT: a wait that exceeds ~4 ms records (block, warp, barrier byte offset, parity) and falls
+// through instead of trapping, so the host can read which hand-off was missed (scripts/bisect_sizes.py).
+#ifdef GDKVM_DEBUG_WAIT
+__device__ unsigned int g_wait_dbg[64 * 4];
+__device__ unsigned int g_wait_dbg_n;
+__device__ __noinline__ void wait_dbg_record(uint64_t* bar, uint32_t parity) {
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned int i = atomicAdd(&g_wait_dbg_n, 1u);
+        if (i < 64) {
+            g_wait_dbg[4 * i] = blockIdx.x; g_wait_dbg[4 * i + 1] = threadIdx.x >> 5;
+            g_wait_dbg[4 * i + 2] = smem_u32(bar); g_wait_dbg[4 * i + 3] = parity;
+        }
+    }
+}
+#define GDKVM_WAIT_TIMEOUT(bar, parity) do { wait_dbg_record(bar, parity); return; } while (0)
+#define GDKVM_WAIT_CYCLES 8000000LL
+#else
+#define GDKVM_WAIT_TIMEOUT(bar, parity) __trap()
+#define GDKVM_WAIT_CYCLES 4000000000LL
+#endif
+
 // Bounded wait: a protocol bug traps (error at the next sync on the host) instead of hanging the GPU.
 // Deliberately not inlined: there are dozens of call sites and the kernel is instruction-fetch sensitive.
+#ifndef GDKVM_SLEEP_WAIT
+#define GDKVM_SLEEP_WAIT 0
+#endif
+#ifndef GDKVM_SLEEP_INL
+#define GDKVM_SLEEP_INL 0
+#endif
 static __device__ __noinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s at 2 GHz
+        if (GDKVM_SLEEP_WAIT) __nanosleep(GDKVM_SLEEP_WAIT);
+        if (clock64() - t0 > GDKVM_WAIT_CYCLES) GDKVM_WAIT_TIMEOUT(bar, parity);   // ~2 s at 2 GHz
     }
 }
 
@@ -59,7 +87,21 @@ __device__ __forceinline__ void mbar_wait_inl(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) __trap();
+        if (GDKVM_SLEEP_INL) __nanosleep(GDKVM_SLEEP_INL);
+        if (clock64() - t0 > GDKVM_WAIT_CYCLES) GDKVM_WAIT_TIMEOUT(bar, parity);
+    }
+}
+
+// Wait with a warp-uniform exit (vote): every lane polls, the loop condition is the VOTE result, so ptxas keeps
+// the issuer warps' loop state and descriptors in uniform registers.
+__device__ __forceinline__ void mbar_wait_u(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+#ifdef GDKVM_DEBUG_WAIT
+        if (++spins > (1u << 16)) GDKVM_WAIT_TIMEOUT(bar, parity);
+#else
+        if (++spins > (1u << 26)) __trap();
+#endif
     }
 }
 
@@ -98,6 +140,7 @@ __device__ __forceinline__ void tma_store_5d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---------------------------------------------------------------- TMEM allocation

@@ -25,17 +25,21 @@ __global__ void __launch_bounds__(128) timing(long long* out, int mode, int N, i
     fence_proxy_async_smem();
     tc_fence_before_sync(); __syncthreads(); tc_fence_after_sync();
     const uint32_t tmem = tmem_s;
-    if (mode == 4 && warp == 0) {          // warp-uniform issue loop, elected lane issues
-        const uint32_t b = smem_u32(smem) + 32768;
-        const uint32_t idesc = umma_idesc_bf16(128, N, false, false);
-        const uint64_t bd0 = umma_smem_desc_sw128(b, 16, 1024);
+    if (mode >= 4 && warp == 0) {          // warp-uniform issue loop, elected lane issues
+        // submode: 4 TS B K-major, 5 TS B MN-major, 6 SS A,B K-major, 7 SS A MN-major (B K-major)
+        const uint32_t a = smem_u32(smem), b = a + 32768;
+        const uint32_t idesc = umma_idesc_bf16(128, N, mode == 7, mode == 5);
+        const uint64_t bd0 = mode == 5 ? umma_smem_desc_sw128(b, 8192, 1024) : umma_smem_desc_sw128(b, 16, 1024);
+        const uint64_t ad0 = mode == 7 ? umma_smem_desc_sw128(a, 8192, 1024) : umma_smem_desc_sw128(a, 16, 1024);
+        const uint32_t bstep = mode == 5 ? 128 : 2, astep = mode == 7 ? 128 : 2;
         uint32_t phase = 0;
         for (int rep = 0; rep < 3; ++rep) {
             const long long t0 = clock64();
             for (int i = 0; i < reps; ++i) {
                 const uint32_t d = tmem + (same_acc ? 0 : (uint32_t)((i & 1) * N));
                 const int k = i & 3;
-                umma_ts_elect(d, tmem + 256 + k * 8, bd0 + (uint64_t)(k * 2), idesc);
+                if (mode < 6) umma_ts_elect(d, tmem + 256 + k * 8, bd0 + (uint64_t)(k * bstep), idesc);
+                else umma_ss_w(d, ad0 + (uint64_t)(k * astep), bd0 + (uint64_t)(k * bstep), idesc, true);
             }
             const long long t1 = clock64();
             if (elect_one()) umma_commit(&bar);
@@ -73,9 +77,10 @@ __global__ void __launch_bounds__(128) timing(long long* out, int mode, int N, i
 int main() {
     long long* d; CK(cudaMalloc(&d, 16));
     CK(cudaFuncSetAttribute(timing, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    const char* names[5] = {"SS A K-major ", "SS A MN-major", "TS B K-major ", "TS B MN-major", "TS uniform-warp issue"};
-    for (int N : {64, 256})
-        for (int mode = 2; mode < 5; mode += 2)
+    const char* names[8] = {"SS A K-major ", "SS A MN-major", "TS B K-major ", "TS B MN-major", "uniform TS B K-major ", "uniform TS B MN-major",
+                            "uniform SS K-major   ", "uniform SS A MN-major"};
+    for (int N : {64, 128})
+        for (int mode = 4; mode < 8; ++mode)
             for (int same = 0; same < 2; ++same) {
                 const int reps = 64;
                 timing<<<1, 128, 100 * 1024>>>(d, mode, N, reps, same);
