@@ -26,8 +26,13 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# BASELINE.json configs[1]
-WORKLOAD = dict(name="echonet_batch", clips=64, frames=128, frame_tokens=49, heads=8, d_k=64, d_v=256)
+# BASELINE.json configs[1] is the bench workload; configs[2] / configs[3] shapes are selectable for extra lines
+WORKLOADS = {
+    "echonet_batch": dict(name="echonet_batch", clips=64, frames=128, frame_tokens=49, heads=8, d_k=64, d_v=256),
+    "camus": dict(name="camus", clips=32, frames=20, frame_tokens=1024, heads=8, d_k=64, d_v=256),
+    "long_clip": dict(name="long_clip", clips=64, frames=256, frame_tokens=49, heads=8, d_k=64, d_v=256),
+}
+WORKLOAD = dict(WORKLOADS["echonet_batch"])
 METRIC = "gdr_memory_frames_per_s"
 UNIT = "frames/s"
 
@@ -173,12 +178,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--flags", type=int, default=0, help="GDKVM_FLAG_* forwarded to the op (1=recurrent, 2=chunked, 4=flat)")
-    ap.add_argument("--clips", type=int, default=WORKLOAD["clips"], help="clips per GPU (default: configs[1])")
+    ap.add_argument("--workload", default="echonet_batch", choices=sorted(WORKLOADS),
+                    help="echonet_batch = BASELINE configs[1] (the bench line); camus / long_clip = configs[2] / [3] shapes per GPU")
+    ap.add_argument("--clips", type=int, default=None, help="clips per GPU (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--compare-fla", action="store_true", help="also time fla's Triton path (informational)")
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
+    WORKLOAD.clear(); WORKLOAD.update(WORKLOADS[args.workload])
+    if args.clips is None:
+        args.clips = WORKLOAD["clips"]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -310,7 +320,7 @@ def main():
     achieved = abytes / (ms_step * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
     kernel = {0: "auto", 1: "gdr_recurrent_kernel (fp32 CUDA cores)", 2: "gdr_chunk_kernel (tcgen05)",
-              6: "gdr_chunk_kernel (tcgen05, flat chunks)"}.get(args.flags, str(args.flags))
+              6: "gdr_chunk_kernel (tcgen05, flat chunks)", 16: "auto, one CTA per chain (no chain splitting)"}.get(args.flags, str(args.flags))
     plan = gdkvm_b200.plan(q, k, v, g, beta, frame_tokens=C, flags=args.flags)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(), "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
@@ -345,7 +355,7 @@ def main():
         "config": {"workload": W["name"], "clips_per_gpu": B, "frames": W["frames"], "frame_tokens": C, "heads": H,
                    "d_k": K, "d_v": V, "tokens_per_clip": T, "flags": args.flags, "kernel": kernel,
                    "arithmetic": "bf16 q/k/v/o and tensor-core operands, fp32 state/accumulators/gates",
-                   "l2": "inputs+outputs per step (4.2 GB) exceed the 126 MB L2; no flush needed",
+                   "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % (abytes / 1e9),
                    "sharding": "clips x heads across ranks, no collective on the hot path"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks,
