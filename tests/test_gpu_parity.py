@@ -137,6 +137,73 @@ def test_state_carry_and_strided_views(op, dtype):
     assert max_rel_err(o3, o_ref) <= TOL[dtype] and max_rel_err(s3, s_ref) <= TOL[dtype]
 
 
+def test_strided_batch_views_on_the_chunk_path(op):
+    """Every other clip of a larger batch (batch stride doubled, nothing copied) through the tcgen05 kernel."""
+    q, k, v, g, beta, S0 = make_inputs(6, 3 * 64 + 9, 2, 64, 256, seed=31, dtype=torch.bfloat16)
+    qd, kd, vd, gd, bd, sd = _dev(q, k, v, g, beta, S0)
+    sl = slice(None, None, 2)
+    assert op.plan(qd[sl], kd[sl], vd[sl], gd[sl], bd[sl]) == 1
+    o, sT = op.gdr_lkva(qd[sl], kd[sl], vd[sl], gd[sl], bd[sl], None, sd[sl].contiguous(), True, 0, CHUNKED)
+    o_c, s_c = op.gdr_lkva(qd[sl].contiguous(), kd[sl].contiguous(), vd[sl].contiguous(), gd[sl].contiguous(),
+                           bd[sl].contiguous(), None, sd[sl].contiguous(), True, 0, CHUNKED)
+    assert torch.equal(o, o_c) and torch.equal(sT, s_c)
+    o_ref, s_ref = gdr_recurrent_ref(q[sl], k[sl], v[sl], g[sl], beta[sl], None, S0[sl])
+    assert max_rel_err(o, o_ref) <= 2e-2 and max_rel_err(sT, s_ref) <= 2e-2
+
+
+def test_frame_aligned_128_token_frames_v128(op):
+    """frame_tokens a multiple of 64 -> frame-aligned sub-chunks by default; V = 128 runs one state warpgroup."""
+    q, k, v, g, beta, S0 = make_inputs(2, 3 * 128, 2, 64, 128, seed=32, frame_tokens=128, correlated=True, dtype=torch.bfloat16)
+    o_ref, s_ref = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    for flags in (CHUNKED, CHUNKED | FLAT, CHUNKED | FRAME):
+        o, sT = _run(op, q, k, v, g, beta, S0, frame_tokens=128, flags=flags)
+        assert max_rel_err(o, o_ref) <= 2e-2 and max_rel_err(sT, s_ref) <= 2e-2, flags
+
+
+def test_strong_decay_takes_the_slow_path(op):
+    """Chunk decay below e^-60 (log-gates scaled up): the per-element exp(Gamma_i - Gamma_j) path of the chunk kernel,
+    mixed with ordinary chunks in the same clip."""
+    q, k, v, g, beta, S0 = make_inputs(2, 5 * 64, 2, 64, 256, seed=33, dtype=torch.bfloat16)
+    g = g.clone()
+    g[:, 64:192] *= 300.0            # chunks 1 and 2: total decay far below e^-60
+    o_ref, s_ref = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    o, sT = _run(op, q, k, v, g, beta, S0, flags=CHUNKED)
+    assert max_rel_err(o, o_ref) <= 2e-2 and max_rel_err(sT, s_ref) <= 2e-2
+
+
+def test_cuda_graph_capture_and_two_streams(op):
+    """The C-ABI call allocates nothing and never syncs: it can be captured into a CUDA graph and replayed, and
+    two problems can run concurrently on two streams."""
+    q, k, v, g, beta, S0 = _dev(*make_inputs(3, 4 * 49, 2, 64, 256, seed=34, frame_tokens=49, dtype=torch.bfloat16))
+    o_ref, s_ref = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 49)
+    o = torch.zeros_like(o_ref); sT = torch.zeros_like(s_ref)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        op.gdr_lkva_out(q, k, v, g, beta, o, sT, None, S0, 49)           # warm-up outside capture
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    o.zero_(); sT.zero_()
+    with torch.cuda.graph(graph):
+        op.gdr_lkva_out(q, k, v, g, beta, o, sT, None, S0, 49)
+    for _ in range(2):
+        o.zero_(); sT.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(o, o_ref) and torch.equal(sT, s_ref)
+    # two streams, two different problems, launched back to back
+    q2, k2, v2, g2, b2, S2 = _dev(*make_inputs(2, 5 * 64, 3, 64, 128, seed=35, dtype=torch.bfloat16))
+    o2_ref, s2_ref = op.gdr_lkva(q2, k2, v2, g2, b2, None, S2, True, 0)
+    s_a, s_b = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s_a):
+        oa, sa = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 49)
+    with torch.cuda.stream(s_b):
+        ob, sb = op.gdr_lkva(q2, k2, v2, g2, b2, None, S2, True, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(oa, o_ref) and torch.equal(sa, s_ref) and torch.equal(ob, o2_ref) and torch.equal(sb, s2_ref)
+
+
 def test_kat_on_device(op):
     """Orthonormal keys, g=0, beta=1: S = sum k_i v_i^T exactly; reading q=k_j returns scale*v_j."""
     K, V = 64, 64
