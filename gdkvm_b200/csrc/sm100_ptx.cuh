@@ -32,8 +32,22 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// GDKVM_TRYWAIT_HINT_NS > 0: pass a suspend-time hint, so a waiting thread sleeps in hardware (up to the hint) instead
+// of coming back to the issue slots of its scheduler every few hundred cycles.
+#ifndef GDKVM_TRYWAIT_HINT_NS
+#define GDKVM_TRYWAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+#if GDKVM_TRYWAIT_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)GDKVM_TRYWAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -41,6 +55,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 // -DGDKVM_DEBUG_WAIT: a wait that exceeds ~4 ms records (block, warp, barrier byte offset, parity) and falls
