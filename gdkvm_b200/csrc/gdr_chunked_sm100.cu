@@ -477,7 +477,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             // (rows past the frame are clipped by the tensor map)
             PT_DECL
             auto readout = [&](int m) {
-                mbar_wait(&bars[kOFull + hh], (uint32_t)m & 1u);
+                mbar_wait_inl(&bars[kOFull + hh], (uint32_t)m & 1u);
                 tc_fence_after_sync();
                 PT(23, tid == 256, m);   // wait: readout accumulators (after Vnb -> state update + intra-chunk MMAs)
                 if (stid == 0) tma_store_wait_read0();      // previous readout has left the staging buffer
@@ -519,7 +519,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             // W^T of chunk m: 8 units of 16 key dims x 32 tokens shared by the state warps (needs the K side of chunk m)
             auto wt_operand = [&](int m) {
                 const int st = m & 1;
-                mbar_wait(&bars[kTpReady + st], (uint32_t)(m >> 1) & 1u);          // K side of chunk m published
+                mbar_wait_inl(&bars[kTpReady + st], (uint32_t)(m >> 1) & 1u);          // K side of chunk m published
                 PT(16, tid == 256, m);   // wait: K side of chunk m
                 const int sw = (warp - 8);                                          // 0 .. 4 NH - 1
                 for (int u = sw; u < (ABL(4) ? 0 : 8); u += 4 * NH)
@@ -535,7 +535,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             wt_operand(0);
             for (int n = 0; n < NC; ++n) {
                 const int st = n & 1;
-                if (n >= 1) mbar_wait(&bars[kSReady + hh], (uint32_t)(n - 1) & 1u);
+                if (n >= 1) mbar_wait_inl(&bars[kSReady + hh], (uint32_t)(n - 1) & 1u);
                 tc_fence_after_sync();
                 PT(17, tid == 256, n);   // wait: state update of chunk n-1
                 {   // S_n = post_{n-1} * accumulator;  Sb = bf16(S_n) (operand copy);  accumulator <- pre_n * S_n
@@ -551,11 +551,11 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
 #pragma unroll
                         for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
                         tmem_st16(lane_addr + kColSb + hh * 32 + half * 16, pk);
-                        if (rescale) {
+                        if (pre != 1.f) {      // slow path only
 #pragma unroll
                             for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * pre);
-                            tmem_st32(lane_addr + kColS + hh * 64 + half * 32, r);
                         }
+                        if (rescale) tmem_st32(lane_addr + kColS + hh * 64 + half * 32, r);
                     }
                     tmem_wait_st();
                 }
@@ -564,7 +564,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 PT(18, tid == 256, n);   // S pass
                 if (n >= 1) readout(n - 1);
                 PT(19, tid == 256, n - 1);   // readout of chunk n-1
-                mbar_wait(&bars[kVnFull + hh], (uint32_t)n & 1u);
+                mbar_wait_inl(&bars[kVnFull + hh], (uint32_t)n & 1u);
                 tc_fence_after_sync();
                 PT(20, tid == 256, n);   // wait: Vn
                 if (!ABL(6)) {   // Vnb = bf16(Vn^T) written over the first half of Vn (TMEM A-operand); both fp32 halves are
@@ -602,7 +602,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 if (n + 1 < NC) wt_operand(n + 1);
             }
             readout(NC - 1);
-            mbar_wait(&bars[kSReady + hh], (uint32_t)(NC - 1) & 1u);
+            mbar_wait_inl(&bars[kSReady + hh], (uint32_t)(NC - 1) & 1u);
             tc_fence_after_sync();
             if (p.final_state != nullptr) {
                 uint32_t r[32];

@@ -73,10 +73,10 @@ __device__ __noinline__ void wait_dbg_record(uint64_t* bar, uint32_t parity) {
     }
 }
 #define GDKVM_WAIT_TIMEOUT(bar, parity) do { wait_dbg_record(bar, parity); return; } while (0)
-#define GDKVM_WAIT_CYCLES 8000000LL
+#define GDKVM_WAIT_POLLS (1u << 16)
 #else
 #define GDKVM_WAIT_TIMEOUT(bar, parity) __trap()
-#define GDKVM_WAIT_CYCLES 4000000000LL
+#define GDKVM_WAIT_POLLS (1u << 26)     // a failed try_wait suspends for ~0.1-1 us: minutes before a protocol bug traps
 #endif
 
 // Bounded wait: a protocol bug traps (error at the next sync on the host) instead of hanging the GPU.
@@ -87,12 +87,14 @@ __device__ __noinline__ void wait_dbg_record(uint64_t* bar, uint32_t parity) {
 #ifndef GDKVM_SLEEP_INL
 #define GDKVM_SLEEP_INL 0
 #endif
+// The time-out counts polls, not clocks: reading the clock (CS2R) goes through the XU pipe, which the fp32 -> bf16
+// packs of this kernel already saturate (ncu: sm__inst_executed_pipe_xu > 100 % of sustained peak).
 static __device__ __noinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (GDKVM_SLEEP_WAIT) __nanosleep(GDKVM_SLEEP_WAIT);
-        if (clock64() - t0 > GDKVM_WAIT_CYCLES) GDKVM_WAIT_TIMEOUT(bar, parity);   // ~2 s at 2 GHz
+        if (++polls > GDKVM_WAIT_POLLS) GDKVM_WAIT_TIMEOUT(bar, parity);
     }
 }
 
@@ -100,10 +102,10 @@ static __device__ __noinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // descriptor out of the uniform registers (R2UR before each UTCHMMA).
 __device__ __forceinline__ void mbar_wait_inl(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (GDKVM_SLEEP_INL) __nanosleep(GDKVM_SLEEP_INL);
-        if (clock64() - t0 > GDKVM_WAIT_CYCLES) GDKVM_WAIT_TIMEOUT(bar, parity);
+        if (++polls > GDKVM_WAIT_POLLS) GDKVM_WAIT_TIMEOUT(bar, parity);
     }
 }
 
@@ -310,11 +312,17 @@ __device__ __forceinline__ void stmatrix_x4_trans(uint32_t addr, uint32_t r0, ui
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-// pack two fp32 into one bf16x2 word: `lo` lands in bits [0,16), `hi` in bits [16,32)
+// pack two fp32 into one bf16x2 word: `lo` lands in bits [0,16), `hi` in bits [16,32).
+// (-DGDKVM_PACK_ALU: integer pack on the ALU pipe, 3 instructions instead of one F2FP -- measured 19 % SLOWER on the
+// whole kernel, which is how the instruction-issue bound of this kernel was confirmed: time follows instruction count.)
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+#ifdef GDKVM_PACK_ALU
+    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+#else
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
+#endif
 }
 
 // byte offset of (row, 16-byte chunk) inside a 128B-swizzled tile whose rows are 128 bytes
