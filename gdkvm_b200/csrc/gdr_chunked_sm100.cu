@@ -287,6 +287,12 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         }
         fence_mbar_init();
     }
+    // H and P are written on and below the diagonal only: the blocks above it stay zero for the whole kernel
+    for (int i = tid; i < 1536; i += kThreads) {
+        if (i < 1024) reinterpret_cast<uint4*>(smem + kOffPp)[i] = make_uint4(0u, 0u, 0u, 0u);
+        else reinterpret_cast<uint4*>(smem + kOffH)[i - 1024] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    fence_proxy_async_smem();
     if (warp == 16) {
         tmem_alloc(s_tmem, kTmemCols);
         if (lane == 0) { tma_prefetch_desc(&mq); tma_prefetch_desc(&mk); tma_prefetch_desc(&mv); tma_prefetch_desc(&mo); }
@@ -353,12 +359,18 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             mbar_wait_inl(&bars[kKqFull], (uint32_t)n & 1u);
             tc_fence_after_sync();
             PT(0, tid == 0, n);   // waits: buffers free, tiles landed, [K;Q]K^T done
-            if (!ABL(0)) {
+            // Warp (wq, wh) holds accumulator rows 32 (wq & 1) .. + 31 of K K^T (wq < 2) or Q K^T and one 32-column half `ch`:
+            // above the diagonal block everything is masked (those tile regions were zeroed once and are never written),
+            // below it nothing is, and only the two diagonal blocks pay for the per-element mask.  Warps 0 and 1 take the
+            // diagonal blocks of K K^T: exactly what levels 0-1 of the solve on the same warp read, so no barrier in between.
+            const int ch = wq == 1 ? (wh ^ 1) : wh;
+            if (!ABL(0) && !((wq & 1) == 0 && ch == 1)) {
                 uint32_t r[32], pk[16];
-                tmem_ld32(lane_addr + kColKQ + wh * 32, r);
+                tmem_ld32(lane_addr + kColKQ + ch * 32, r);
                 tmem_wait_ld();
-                const int j0 = wh * 32;
+                const int j0 = ch * 32;
                 const float* Gm = sGam + st * 64;
+                const bool diag = (wq & 1) == ch;
                 if (!fast) {           // rare: per-element decay exp(Gamma_i - Gamma_j) (and the readout scale) applied first
                     const int i = (wq & 1) * 32 + lane;
                     const float gi = Gm[i], sc = wq < 2 ? 1.f : scale;
@@ -384,24 +396,30 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 if (wq < 2) {          // rows of K K^T:  A_ij = beta_i (k_i.k_j),  j < i
                     const int i = wq * 32 + lane;
                     const float bi = btS[i];
+                    if (diag) {
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) {
-                        const int j = j0 + 2 * jj;
-                        pk[jj] = tri::pack_f16(j < i ? __uint_as_float(r[2 * jj]) * bi : 0.f, j + 1 < i ? __uint_as_float(r[2 * jj + 1]) * bi : 0.f);
+                        for (int jj = 0; jj < 16; ++jj)
+                            pk[jj] = tri::pack_f16(2 * jj < lane ? __uint_as_float(r[2 * jj]) * bi : 0.f, 2 * jj + 1 < lane ? __uint_as_float(r[2 * jj + 1]) * bi : 0.f);
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) pk[jj] = tri::pack_f16(__uint_as_float(r[2 * jj]) * bi, __uint_as_float(r[2 * jj + 1]) * bi);
                     }
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
-                        *reinterpret_cast<uint4*>(sH + sw128_offset(i, wh * 4 + c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                        *reinterpret_cast<uint4*>(sH + sw128_offset(i, ch * 4 + c)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                 } else {               // rows of Q K^T:  P_ij = (q_i.k_j),  j <= i   (fast: scale e_i is applied in the readout)
                     const int i = (wq - 2) * 32 + lane;
+                    if (diag) {
 #pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) {
-                        const int j = j0 + 2 * jj;
-                        pk[jj] = pack_bf16(j <= i ? __uint_as_float(r[2 * jj]) : 0.f, j + 1 <= i ? __uint_as_float(r[2 * jj + 1]) : 0.f);
+                        for (int jj = 0; jj < 16; ++jj)
+                            pk[jj] = pack_bf16(2 * jj <= lane ? __uint_as_float(r[2 * jj]) : 0.f, 2 * jj + 1 <= lane ? __uint_as_float(r[2 * jj + 1]) : 0.f);
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) pk[jj] = pack_bf16(__uint_as_float(r[2 * jj]), __uint_as_float(r[2 * jj + 1]));
                     }
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
-                        *reinterpret_cast<uint4*>(smem + kOffPp + st * 8192 + sw128_offset(i, wh * 4 + c)) =
+                        *reinterpret_cast<uint4*>(smem + kOffPp + st * 8192 + sw128_offset(i, ch * 4 + c)) =
                             make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
                 }
             }
@@ -417,36 +435,42 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 }
             }
             PT(1, tid == 0, n);   // gating (own work)
-            kbar();
-            PT(2, tid == 0, n);   // gating (barrier wait)
 
-            // (I + A)^-1 in place: levels 0-1 on warps 0-1, level 2 on warps 0-3; warp 7 scans the gates of chunk n+1
-            if (warp < 2 && !ABL(1)) tri::solve_levels01(sH, aH, warp, lane);
-            PT(3, tid == 0, n);   // diagonal blocks + level 1
-            if (warp < 4) {
-                named_bar_sync(5, 128);
-                if (!ABL(2)) tri::solve_level2(aH, warp, lane, 5); else named_bar_sync(5, 128);
+            // (I + A)^-1 in place.  Levels 0-1 on warps 0-1 straight after their own gating (they wrote the diagonal 32 x 32
+            // blocks themselves); warp 7 scans the gates of chunk n+1 meanwhile.
+            if (warp < 2) {
+                __syncwarp();
+                if (!ABL(1)) tri::solve_levels01(sH, aH, warp, lane);
             } else if (warp == 7 && n + 1 < NC) {
                 scan_chunk(n + 1, g_nx, b_nx);
                 if (n + 2 < NC) load_gates(n + 2, g_nx, b_nx);
             }
+            PT(3, tid == 0, n);   // diagonal blocks + level 1
+            kbar();                // A complete (all eight warps), levels 0-1 done
+            PT(2, tid == 0, n);   // barrier before level 2
+            // T' = X diag(c) -> bf16, K-major swizzled rows: H and T' share one layout (thread: one 16-byte chunk per task)
+            auto convert_rows = [&](int task) {
+                const float* cjS = sCj + st * 64;
+                const int i = task >> 3, c = task & 7;
+                const uint32_t off = sw128_offset(i, c);
+                const uint4 hx = *reinterpret_cast<const uint4*>(sH + off);
+                const float4 c0 = *reinterpret_cast<const float4*>(cjS + c * 8), c1 = *reinterpret_cast<const float4*>(cjS + c * 8 + 4);
+                const float2 x0 = tri::unpack_f16(hx.x), x1 = tri::unpack_f16(hx.y), x2 = tri::unpack_f16(hx.z), x3 = tri::unpack_f16(hx.w);
+                *reinterpret_cast<uint4*>(smem + kOffTp + st * 8192 + off) =
+                    make_uint4(pack_bf16(x0.x * c0.x, x0.y * c0.y), pack_bf16(x1.x * c0.z, x1.y * c0.w),
+                               pack_bf16(x2.x * c1.x, x2.y * c1.y), pack_bf16(x3.x * c1.z, x3.y * c1.w));
+            };
+            // Level 2 (warps 0-3) only writes rows 32-63, columns 0-31: rows 0-31 of X are final, warps 4-7 convert them now
+            if (warp < 4) {
+                if (!ABL(2)) tri::solve_level2(aH, warp, lane, 5); else named_bar_sync(5, 128);
+            } else if (!ABL(3)) {
+                convert_rows(tid - 128);            // tasks 0 .. 255: rows 0-31
+                convert_rows(tid);
+            }
             PT(4, tid == 0, n);   // level 2
             kbar();
             PT(5, tid == 0, n);   // solve barrier
-            {   // T' = X diag(c) -> bf16, K-major swizzled rows: H and T' share one layout (thread: one 16-byte chunk, 2 tasks)
-                const float* cjS = sCj + st * 64;
-#pragma unroll
-                for (int it = 0; it < (ABL(3) ? 0 : 2); ++it) {
-                    const int task = it * kKThreads + tid, i = task >> 3, c = task & 7;
-                    const uint32_t off = sw128_offset(i, c);
-                    const uint4 hx = *reinterpret_cast<const uint4*>(sH + off);
-                    const float4 c0 = *reinterpret_cast<const float4*>(cjS + c * 8), c1 = *reinterpret_cast<const float4*>(cjS + c * 8 + 4);
-                    const float2 x0 = tri::unpack_f16(hx.x), x1 = tri::unpack_f16(hx.y), x2 = tri::unpack_f16(hx.z), x3 = tri::unpack_f16(hx.w);
-                    *reinterpret_cast<uint4*>(smem + kOffTp + st * 8192 + off) =
-                        make_uint4(pack_bf16(x0.x * c0.x, x0.y * c0.y), pack_bf16(x1.x * c0.z, x1.y * c0.w),
-                                   pack_bf16(x2.x * c1.x, x2.y * c1.y), pack_bf16(x3.x * c1.z, x3.y * c1.w));
-                }
-            }
+            if (!ABL(3)) convert_rows(256 + tid);   // rows 32-63, one task per thread
             fence_proxy_async_smem();
             kbar();
             PT(6, tid == 0, n);   // T' conversion

@@ -101,12 +101,30 @@ static __device__ __noinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Inlined wait for the MMA/TMA issuer warps: a CALL in their loops would force every loop-invariant
 // descriptor out of the uniform registers (R2UR before each UTCHMMA).
 __device__ __forceinline__ void mbar_wait_inl(uint64_t* bar, uint32_t parity) {
+#if defined(GDKVM_DEBUG_WAIT) || GDKVM_SLEEP_INL
     if (mbar_try_wait(bar, parity)) return;
     uint32_t polls = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (GDKVM_SLEEP_INL) __nanosleep(GDKVM_SLEEP_INL);
         if (++polls > GDKVM_WAIT_POLLS) GDKVM_WAIT_TIMEOUT(bar, parity);
     }
+#else
+    // one PTX block (labels are local to the braces): three instructions when the phase has already completed --
+    // the kernel is instruction-issue bound and executes ~70 warp-level waits per chunk
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 p, c, %2;\n\t"
+        "@p bra WAIT_LOOP;\n\t"
+        "trap;\n"
+        "WAIT_DONE:\n\t}\n"
+        ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)GDKVM_WAIT_POLLS)
+        : "memory");
+#endif
 }
 
 // Wait with a warp-uniform exit (vote): every lane polls, the loop condition is the VOTE result, so ptxas keeps
