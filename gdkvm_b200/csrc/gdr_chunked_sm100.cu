@@ -246,10 +246,28 @@ __device__ __forceinline__ void umma4_ts(uint32_t d, uint32_t a_tmem, uint64_t b
     for (int k = 0; k < 4; ++k) umma_ts_w(d, a_tmem + k * 8, bdesc + (uint64_t)(k * bstep), idesc, acc0 || k > 0);
 }
 
+// n / d for 0 <= n < 2^31 and a run-time d >= 1 without the ~40-instruction integer division sequence (the kernel is
+// instruction-issue bound and maps chunk -> (frame, chunk in frame) several times per chunk).  Host-side constants.
+struct FastDiv {
+    unsigned int mul, shr, d;
+    __host__ static FastDiv make(unsigned int d) {
+        FastDiv f{0u, 0u, d};
+        if (d > 1) {
+            unsigned int l = 0;
+            while ((1ull << l) < d) ++l;                              // ceil(log2 d)
+            const unsigned long long p = 31 + l;
+            f.mul = (unsigned int)(((1ull << p) + d - 1) / d);        // ceil(2^p / d) < 2^32
+            f.shr = (unsigned int)(p - 32);
+        }
+        return f;
+    }
+    __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((unsigned int)n, mul) >> shr); }
+};
+
 __global__ void __launch_bounds__(kThreads, 1)
 gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                  const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mo,
-                 const GdkvmGdrParams p, const int C, const int F) {
+                 const GdkvmGdrParams p, const int C, const int F, const FastDiv div_cpf) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-align inside the shared window with pointer arithmetic only (an integer round trip would
     // demote every access below from LDS/STS to generic LD/ST)
@@ -321,7 +339,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         const int64_t g_off = (int64_t)b * p.g_stride[0] + (int64_t)h * p.g_stride[2];
         const int64_t bt_off = (int64_t)b * p.beta_stride[0] + (int64_t)h * p.beta_stride[2];
         auto load_gates = [&](int n, float (&gv)[2], float (&bv)[2]) {
-            const int f = n / cpf;
+            const int f = div_cpf.div(n);
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int c = ((n - f * cpf) << 6) + 2 * lane + e;
@@ -535,7 +553,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 fence_proxy_async_smem();
                 named_bar_sync(bar_id, 128);
                 if (stid == 0) {
-                    const int f = m / cpf, c0 = (m - f * cpf) << 6;
+                    const int f = div_cpf.div(m), c0 = (m - f * cpf) << 6;
                     tma_store_5d(&mo, smem + kOffOst + hh * 16384, 0, c0, h * VB + hh * 2, f, b);
                     tma_store_commit();
                 }
@@ -617,7 +635,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 tc_fence_before_sync();
                 mbar_arrive(&bars[kVnbReady + hh]);
                 if (stid == 0 && n + 2 < NC) {   // U of chunk n is complete: its V half-tile slot takes chunk n + 2
-                    const int m = n + 2, f = m / cpf, c0 = (m - f * cpf) << 6;
+                    const int m = n + 2, f = div_cpf.div(m), c0 = (m - f * cpf) << 6;
                     uint64_t* vb = &bars[kVTile + st * 2 + hh];
                     mbar_arrive_expect_tx(vb, 16384u);
                     tma_load_5d(smem + kOffV + st * kVSlotBytes + hh * 16384, &mv, vb, 0, c0, h * VB + hh * 2, f, b);
@@ -649,7 +667,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         // =========================================================================================
         {
             auto issue_kq = [&](int m) {         // one elected lane arms the barrier and issues the K and Q tile loads
-                const int slot = m % 3, f = m / cpf, c0 = (m - f * cpf) << 6;
+                const int slot = m % 3, f = div_cpf.div(m), c0 = (m - f * cpf) << 6;
                 uint8_t* sp = smem + kOffKq + (uint32_t)slot * kKqSlotBytes;
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&bars[kKqTile + slot], 16384u);
@@ -661,7 +679,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             for (int m = 0; m < 2 && m < NC; ++m) {      // prologue: chunks 0 and 1 (their V tiles too)
                 issue_kq(m);
                 if (elect_one()) {
-                    const int f = m / cpf, c0 = (m - f * cpf) << 6;
+                    const int f = div_cpf.div(m), c0 = (m - f * cpf) << 6;
                     for (int hh = 0; hh < NH; ++hh) {
                         uint64_t* vb = &bars[kVTile + m * 2 + hh];
                         mbar_arrive_expect_tx(vb, 16384u);
@@ -822,7 +840,7 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
         if (rc == 0) rc = make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.o, dims, so, boxo, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc != 0) return (int)cudaErrorInvalidValue;
     }
-    gdr_chunk_kernel<<<p.B * p.H, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, C, F);
+    gdr_chunk_kernel<<<p.B * p.H, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, C, F, FastDiv::make((unsigned)((C + 63) / 64)));
     count_launch();
     return (int)cudaGetLastError();
 }
