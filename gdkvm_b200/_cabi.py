@@ -14,7 +14,7 @@ FLAG_FORCE_RECURRENT, FLAG_FORCE_CHUNKED, FLAG_FLAT_CHUNKS, FLAG_FRAME_CHUNKS = 
 
 EXPORTED_SYMBOLS = (
     "gdkvm_abi_version", "gdkvm_strerror", "gdkvm_last_cuda_error",
-    "gdkvm_gdr_fwd", "gdkvm_gdr_plan", "gdkvm_launch_count",
+    "gdkvm_gdr_fwd", "gdkvm_gdr_plan", "gdkvm_launch_count", "gdkvm_l2norm_fwd",
 )
 
 
@@ -57,6 +57,9 @@ def load() -> ctypes.CDLL:
             lib.gdkvm_gdr_plan.restype = ctypes.c_int
             lib.gdkvm_gdr_plan.argtypes = [ctypes.POINTER(GdkvmGdrParams)]
             lib.gdkvm_launch_count.restype = ctypes.c_uint64
+            lib.gdkvm_l2norm_fwd.restype = ctypes.c_int
+            lib.gdkvm_l2norm_fwd.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
+                                             ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]
             if lib.gdkvm_abi_version() != GDKVM_ABI_VERSION:
                 raise RuntimeError("libgdkvm_gdr.so ABI version mismatch; rebuild")
             _lib = lib

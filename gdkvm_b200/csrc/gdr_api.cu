@@ -100,6 +100,25 @@ int gdkvm_gdr_plan(const GdkvmGdrParams* params) {
     return gdkvm::pick(params);
 }
 
+int gdkvm_l2norm_fwd(const void* x, void* y, int64_t rows, int32_t D, int64_t x_row_stride, int64_t y_row_stride,
+                     int32_t dtype, float eps, void* cuda_stream) {
+    if (rows < 0 || (D != 32 && D != 64 && D != 128 && D != 256)) return GDKVM_ERR_SHAPE;
+    if (dtype != GDKVM_F32 && dtype != GDKVM_BF16) return GDKVM_ERR_DTYPE;
+    if (rows == 0) return GDKVM_OK;
+    if (x == nullptr || y == nullptr) return GDKVM_ERR_NULL;
+    const int64_t es = dtype == GDKVM_BF16 ? 2 : 4;
+    if ((reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(y) & 15u) || (x_row_stride * es) % 16 != 0 ||
+        (y_row_stride * es) % 16 != 0 || x_row_stride < D || y_row_stride < D)
+        return GDKVM_ERR_ALIGN;
+    bool sm100 = false;
+    int ce = gdkvm::device_is_sm100(&sm100);
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    if (!sm100) return GDKVM_ERR_ARCH;
+    ce = gdkvm::launch_l2norm(x, y, rows, D, x_row_stride, y_row_stride, dtype, eps, reinterpret_cast<cudaStream_t>(cuda_stream));
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    return GDKVM_OK;
+}
+
 int gdkvm_gdr_fwd(const GdkvmGdrParams* params, void* cuda_stream) {
     int rc = gdkvm::validate(params);
     if (rc != GDKVM_OK) return rc;

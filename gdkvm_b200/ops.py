@@ -22,7 +22,7 @@ import torch
 
 from . import _cabi
 
-__all__ = ["gdr_lkva", "gdr_lkva_out", "chunk_gated_delta_rule", "plan", "launch_count"]
+__all__ = ["gdr_lkva", "gdr_lkva_out", "chunk_gated_delta_rule", "l2norm", "plan", "launch_count"]
 
 _DT = {torch.float32: _cabi.GDKVM_F32, torch.bfloat16: _cabi.GDKVM_BF16}
 
@@ -133,6 +133,38 @@ def _gdr_lkva_fake(q, k, v, g, beta, scale=None, initial_state=None, output_fina
     return o, sT
 
 
+torch.library.define("gdkvm::l2norm", "(Tensor x, float eps=1e-6) -> Tensor")
+
+
+@torch.library.impl("gdkvm::l2norm", "CUDA")
+def _l2norm_cuda(x, eps=1e-6):
+    if x.dtype not in _DT:
+        raise TypeError("l2norm: x must be float32 or bfloat16")
+    D = x.shape[-1]
+    xc = x if x.is_contiguous() else x.contiguous()
+    y = torch.empty_like(xc)
+    rows = xc.numel() // D if D else 0
+    lib = _cabi.load()
+    with torch.cuda.device(x.device):
+        rc = lib.gdkvm_l2norm_fwd(ctypes.c_void_p(xc.data_ptr()), ctypes.c_void_p(y.data_ptr()), rows, D, D, D, _DT[x.dtype],
+                                  float(eps), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        extra = f" (cudaError {lib.gdkvm_last_cuda_error()})" if rc == -7 else ""
+        raise RuntimeError(f"gdkvm_l2norm_fwd: {_cabi.strerror(rc)}{extra}")
+    return y
+
+
+@torch.library.register_fake("gdkvm::l2norm")
+def _l2norm_fake(x, eps=1e-6):
+    return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+
+def l2norm(x: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """Row-wise ``x * rsqrt(sum(x^2, -1) + eps)`` on the B200 (the q/k normalisation in front of the memory op;
+    fla's ``use_qk_l2norm_in_kernel``, fla/ops/gated_delta_rule/chunk.py:374).  D in {32, 64, 128, 256}."""
+    return torch.ops.gdkvm.l2norm(x, eps)
+
+
 def gdr_lkva(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, g: torch.Tensor, beta: torch.Tensor,
              scale: Optional[float] = None, initial_state: Optional[torch.Tensor] = None,
              output_final_state: bool = True, frame_tokens: int = 0,
@@ -152,9 +184,11 @@ def chunk_gated_delta_rule(q, k, v, g, beta, scale=None, initial_state=None, out
                            **kwargs):
     """Name- and argument-compatible alias of fla's entry point (fla/ops/gated_delta_rule/chunk.py:365)."""
     unsupported = {kk: vv for kk, vv in kwargs.items()
-                   if kk not in ("frame_tokens", "flags") and vv is not None and vv is not False}
+                   if kk not in ("frame_tokens", "flags", "use_qk_l2norm_in_kernel") and vv is not None and vv is not False}
     if unsupported:
         raise NotImplementedError(f"gdkvm_b200.chunk_gated_delta_rule: unsupported arguments {sorted(unsupported)}")
+    if kwargs.get("use_qk_l2norm_in_kernel"):      # one streaming CUDA pass each (not yet fused into the chunk kernel)
+        q, k = l2norm(q), l2norm(k)
     return gdr_lkva(q, k, v, g, beta, scale, initial_state, output_final_state,
                     kwargs.get("frame_tokens", 0), kwargs.get("flags", 0))
 

@@ -113,6 +113,16 @@ int gdkvm_gdr_fwd(const GdkvmGdrParams* params, void* cuda_stream);
  */
 int gdkvm_gdr_plan(const GdkvmGdrParams* params);
 
+/*
+ * Row-wise L2 normalisation  y[r][:] = x[r][:] * rsqrt(sum(x[r][:]^2) + eps)  of `rows` rows of D elements (dtype:
+ * GdkvmDtype; D in {32, 64, 128, 256}; row strides in ELEMENTS, multiples of 16 bytes; 16-byte aligned bases; y may
+ * alias x).  The step immediately before the memory op when the caller asks for normalised q / k:
+ *   replaces: fla's `use_qk_l2norm_in_kernel=True` (fla/ops/gated_delta_rule/chunk.py:374); SURVEY.md section 8f rank 3.
+ * Asynchronous on `cuda_stream`; 0 or a negative GdkvmStatus.
+ */
+int gdkvm_l2norm_fwd(const void* x, void* y, int64_t rows, int32_t D, int64_t x_row_stride, int64_t y_row_stride,
+                     int32_t dtype, float eps, void* cuda_stream);
+
 /* Number of kernels this library has launched in the calling process (bench "gpu_launches"). */
 uint64_t gdkvm_launch_count(void);
 

@@ -204,6 +204,34 @@ def test_cuda_graph_capture_and_two_streams(op):
     assert torch.equal(oa, o_ref) and torch.equal(sa, s_ref) and torch.equal(ob, o2_ref) and torch.equal(sb, s2_ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("D", [32, 64, 128, 256])
+def test_l2norm_prologue(op, dtype, D):
+    """q/k normalisation kernel against x * rsqrt(sum x^2 + eps) in fp32 (the result rounded to the I/O dtype)."""
+    g = torch.Generator().manual_seed(40 + D)
+    x = (torch.randn(3, 37, 5, D, generator=g) * torch.rand(3, 37, 5, 1, generator=g) * 4).to(dtype)
+    ref = (x.float() * torch.rsqrt(x.float().square().sum(-1, keepdim=True) + 1e-6)).to(dtype)
+    y = op.l2norm(x.cuda())
+    torch.cuda.synchronize()
+    assert y.dtype == dtype and y.shape == x.shape
+    tol = 1e-6 if dtype == torch.float32 else 2.0 ** -8      # one bf16 ulp of values <= 1
+    assert (y.cpu().float() - ref.float()).abs().max().item() <= tol
+    z = torch.zeros(4, D, dtype=dtype, device="cuda")          # zero rows stay zero (eps)
+    assert torch.equal(op.l2norm(z), z)
+
+
+def test_chunk_gated_delta_rule_with_qk_l2norm(op):
+    """fla's use_qk_l2norm_in_kernel=True: unnormalised q, k in, same result as normalising first."""
+    q, k, v, g, beta, S0 = make_inputs(2, 3 * 49, 2, 64, 256, seed=41, frame_tokens=49, dtype=torch.bfloat16)
+    q = (q.float() * 3.0).bfloat16(); k = (k.float() * 0.5).bfloat16()
+    qd, kd, vd, gd, bd, sd = _dev(q, k, v, g, beta, S0)
+    o, sT = op.chunk_gated_delta_rule(qd, kd, vd, gd, bd, initial_state=sd, output_final_state=True, use_qk_l2norm_in_kernel=True)
+    qn = (q.float() * torch.rsqrt(q.float().square().sum(-1, keepdim=True) + 1e-6)).bfloat16()
+    kn = (k.float() * torch.rsqrt(k.float().square().sum(-1, keepdim=True) + 1e-6)).bfloat16()
+    o_ref, s_ref = gdr_recurrent_ref(qn, kn, v, g, beta, None, S0)
+    assert max_rel_err(o, o_ref) <= 2e-2 and max_rel_err(sT, s_ref) <= 2e-2
+
+
 def test_kat_on_device(op):
     """Orthonormal keys, g=0, beta=1: S = sum k_i v_i^T exactly; reading q=k_j returns scale*v_j."""
     K, V = 64, 64
