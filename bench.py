@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--flags", type=int, default=0, help="GDKVM_FLAG_* forwarded to the op (1=recurrent, 2=chunked, 4=flat)")
+    ap.add_argument("--flags", type=int, default=0, help="GDKVM_FLAG_* forwarded to the op (1=recurrent, 2=chunked, 4=flat, 8=frame chunks, n<<8 = n time segments)")
     ap.add_argument("--workload", default="echonet_batch", choices=sorted(WORKLOADS),
                     help="echonet_batch = BASELINE configs[1] (the bench line); camus / long_clip = configs[2] / [3] shapes per GPU")
     ap.add_argument("--clips", type=int, default=None, help="clips per GPU (default: the workload's)")
@@ -320,8 +320,10 @@ def main():
     achieved = abytes / (ms_step * 1e-3) / 1e9
     peak, peak_src = measured_peak_gbs()
     kernel = {0: "auto", 1: "gdr_recurrent_kernel (fp32 CUDA cores)", 2: "gdr_chunk_kernel (tcgen05)",
-              6: "gdr_chunk_kernel (tcgen05, flat chunks)", 16: "auto, one CTA per chain (no chain splitting)"}.get(args.flags, str(args.flags))
+              6: "gdr_chunk_kernel (tcgen05, flat chunks)"}.get(args.flags & 0xff, str(args.flags))
     plan = gdkvm_b200.plan(q, k, v, g, beta, frame_tokens=C, flags=args.flags)
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    segments = gdkvm_b200.plan_segments(q, k, v, g, beta, frame_tokens=C, flags=args.flags, sm_count=sms)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(), "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
                 "kernel": "gdr_chunk_kernel (tcgen05)" if plan == 1 else "gdr_recurrent_kernel (fp32 CUDA cores)",
@@ -354,6 +356,7 @@ def main():
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": W["name"], "clips_per_gpu": B, "frames": W["frames"], "frame_tokens": C, "heads": H,
                    "d_k": K, "d_v": V, "tokens_per_clip": T, "flags": args.flags, "kernel": kernel,
+                   "time_segments": f"{segments} per (clip, head) chain: {B * H * segments} work units on {sms} SMs",
                    "arithmetic": "bf16 q/k/v/o and tensor-core operands, fp32 state/accumulators/gates",
                    "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % (abytes / 1e9),
                    "sharding": "clips x heads across ranks, no collective on the hot path"},

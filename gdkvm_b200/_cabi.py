@@ -12,9 +12,14 @@ GDKVM_ABI_VERSION = 1
 GDKVM_F32, GDKVM_BF16 = 0, 1
 FLAG_FORCE_RECURRENT, FLAG_FORCE_CHUNKED, FLAG_FLAT_CHUNKS, FLAG_FRAME_CHUNKS = 0x1, 0x2, 0x4, 0x8
 
+
+def FLAG_SEGMENTS(n: int) -> int:
+    """GDKVM_FLAG_SEGMENTS(n): cut every chain into n (1..15) time segments; 0 = the library chooses."""
+    return (int(n) & 0xF) << 8
+
 EXPORTED_SYMBOLS = (
     "gdkvm_abi_version", "gdkvm_strerror", "gdkvm_last_cuda_error",
-    "gdkvm_gdr_fwd", "gdkvm_gdr_plan", "gdkvm_launch_count", "gdkvm_l2norm_fwd",
+    "gdkvm_gdr_fwd", "gdkvm_gdr_plan", "gdkvm_gdr_plan_segments", "gdkvm_launch_count", "gdkvm_l2norm_fwd",
 )
 
 
@@ -56,6 +61,8 @@ def load() -> ctypes.CDLL:
             lib.gdkvm_gdr_fwd.argtypes = [ctypes.POINTER(GdkvmGdrParams), ctypes.c_void_p]
             lib.gdkvm_gdr_plan.restype = ctypes.c_int
             lib.gdkvm_gdr_plan.argtypes = [ctypes.POINTER(GdkvmGdrParams)]
+            lib.gdkvm_gdr_plan_segments.restype = ctypes.c_int
+            lib.gdkvm_gdr_plan_segments.argtypes = [ctypes.POINTER(GdkvmGdrParams), ctypes.c_int]
             lib.gdkvm_launch_count.restype = ctypes.c_uint64
             lib.gdkvm_l2norm_fwd.restype = ctypes.c_int
             lib.gdkvm_l2norm_fwd.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,

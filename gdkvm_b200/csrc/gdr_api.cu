@@ -100,6 +100,13 @@ int gdkvm_gdr_plan(const GdkvmGdrParams* params) {
     return gdkvm::pick(params);
 }
 
+int gdkvm_gdr_plan_segments(const GdkvmGdrParams* params, int sm_count) {
+    const int rc = gdkvm::validate(params);
+    if (rc != GDKVM_OK) return rc;
+    if (params->T == 0 || gdkvm::pick(params) != 1) return 1;
+    return gdkvm::chunked_segments(*params, sm_count);
+}
+
 int gdkvm_l2norm_fwd(const void* x, void* y, int64_t rows, int32_t D, int64_t x_row_stride, int64_t y_row_stride,
                      int32_t dtype, float eps, void* cuda_stream) {
     if (rows < 0 || (D != 32 && D != 64 && D != 128 && D != 256)) return GDKVM_ERR_SHAPE;

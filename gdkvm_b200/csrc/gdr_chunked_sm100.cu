@@ -35,9 +35,22 @@
 // so the fast path never rescales a tile in shared memory.  Chunks with stronger decay use the
 // per-element exp(Gamma_i - Gamma_j) form (slow path, rare): same MMA sequence, tiles rescaled in place.
 //
+// Time segments.  One CTA per chain leaves a ragged last wave (512 chains on 148 SMs: 3.46 waves, the fourth one 46 %
+// full).  A chain is therefore cut at chunk boundaries into `nseg` segments that are separate work units: unit
+// u = seg * chains + chain, taken in ticket order (an atomic counter, so a unit's predecessor is always resident or
+// done).  A segment hands its fp32 state to the next one through a per-launch scratch buffer in global memory
+// (64 KiB per chain, released by a flag); the arithmetic is the one of an uncut chain, bit for bit.  The host picks
+// nseg by simulating the unit schedule (pick_segments).
+//
 // Layout facts used here were verified on hardware by tests/probes/umma_probe.cu.
 // Math: oracle/gdr_ref.py::gdr_chunk_ref.
+#include <algorithm>
+#include <functional>
+#include <map>
 #include <mutex>
+#include <queue>
+#include <tuple>
+#include <vector>
 
 #include "gdr_common.cuh"
 #include "sm100_ptx.cuh"
@@ -69,7 +82,7 @@ constexpr uint32_t kOffF = kOffH + 8192;
 constexpr uint32_t kNumFloats = 18 * 64 + 12;
 constexpr uint32_t kOffBar = kOffF + kNumFloats * 4;
 constexpr uint32_t kNumBars = 27;
-constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 16 + 1024;   // + tmem slot + alignment slack
+constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 32 + 1024;   // + tmem slot + unit info + alignment slack
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
 // ---- tensor memory map (columns) ----
@@ -267,7 +280,8 @@ struct FastDiv {
 __global__ void __launch_bounds__(kThreads, 1)
 gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                  const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mo,
-                 const GdkvmGdrParams p, const int C, const int F, const FastDiv div_cpf) {
+                 const GdkvmGdrParams p, const int C, const int F, const FastDiv div_cpf,
+                 const int nseg, const int seg_chunks, float* __restrict__ xstate, int* __restrict__ xsync) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-align inside the shared window with pointer arithmetic only (an integer round trip would
     // demote every access below from LDS/STS to generic LD/ST)
@@ -284,14 +298,22 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     float* sFast = sPre + 4;                              // [4] chunk n in slot n & 3
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
+    // work unit of this CTA, written once by thread 0: [0] time segment [1] chain [2] clip [3] head [4] first chunk.
+    // Read through a volatile pointer where it is used (single threads, outside the hot loops) so that
+    // none of it occupies registers of the instruction-bound warps for the whole kernel.
+    volatile int* s_info = reinterpret_cast<volatile int*>(s_tmem + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int chain = blockIdx.x, b = chain / p.H, h = chain % p.H;
     const int V = p.V, NH = V >> 7, VB = V >> 6;
-    const int cpf = (C + 63) >> 6, NC = F * cpf;
+    const int cpf = (C + 63) >> 6;
     const float scale = p.scale;
 
     if (tid == 0) {
+        // unit -> (time segment, chain), in ticket order when chains are cut in time
+                const int unit = nseg > 1 ? atomicAdd(xsync, 1) : (int)blockIdx.x, nchains = p.B * p.H;
+        const int seg = unit / nchains, chain = unit - seg * nchains, clip = chain / p.H, nb = seg * seg_chunks;
+        s_info[0] = seg; s_info[1] = chain; s_info[2] = clip; s_info[3] = chain - clip * p.H;
+        s_info[4] = nb;
         for (int i = 0; i < 3; ++i) mbar_init(&bars[kKqTile + i], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&bars[kVTile + i], 1);
         mbar_init(&bars[kKqFull], 1); mbar_init(&bars[kKqFree], kKThreads);
@@ -319,6 +341,15 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem = *s_tmem;
+    // Chunks s_info[4] .. + NC - 1 of the chain; n below counts inside the segment.  NC is the same for every unit (a
+    // kernel parameter, so every loop bound stays warp-uniform for the compiler); chunks past the end of the chain in
+    // the last segment are exact no-ops: tiles zero-filled by TMA, gates 0, stores clipped.
+    const int NC = seg_chunks, nc_chain = F * cpf;
+#define U_SEG s_info[0]
+#define U_CHAIN s_info[1]
+#define U_CLIP s_info[2]
+#define U_HEAD s_info[3]
+#define U_NB s_info[4]
 
     constexpr uint32_t kIdKK = umma_idesc_bf16(128, 64, false, false);
     constexpr uint32_t kIdMnA = umma_idesc_bf16(128, 64, true, false);          // A = tile^T (MN-major), B K-major
@@ -336,15 +367,15 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         // warp 7 owns the gates: it holds g, beta of the NEXT chunk in registers (loaded one chunk period
         // before they are scanned, so the global-load latency never stalls the group) and scans them while
         // warps 0-3 run the triangular solve.  Lane l: tokens 2l, 2l+1 of the chunk.
-        const int64_t g_off = (int64_t)b * p.g_stride[0] + (int64_t)h * p.g_stride[2];
-        const int64_t bt_off = (int64_t)b * p.beta_stride[0] + (int64_t)h * p.beta_stride[2];
+        const int64_t g_off = (int64_t)U_CLIP * p.g_stride[0] + (int64_t)U_HEAD * p.g_stride[2];
+        const int64_t bt_off = (int64_t)U_CLIP * p.beta_stride[0] + (int64_t)U_HEAD * p.beta_stride[2];
         auto load_gates = [&](int n, float (&gv)[2], float (&bv)[2]) {
-            const int f = div_cpf.div(n);
+            const int m = U_NB + n, f = div_cpf.div(m);
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int c = ((n - f * cpf) << 6) + 2 * lane + e;
+                const int c = ((m - f * cpf) << 6) + 2 * lane + e;
                 gv[e] = 0.f; bv[e] = 0.f;                        // pad rows: exact no-ops
-                if (c < C) {
+                if (c < C && m < nc_chain) {
                     const int64_t t = (int64_t)f * C + c;
                     gv[e] = load_gate(p.g, g_off + t * p.g_stride[1], p.gate_dtype);
                     bv[e] = load_gate(p.beta, bt_off + t * p.beta_stride[1], p.gate_dtype);
@@ -503,13 +534,26 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
             const int vcol = hh * 128 + wq * 32 + lane;
             const int bar_id = 2 + hh;
-            {   // initial state -> TMEM
+            {   // initial state -> TMEM: the caller's for the first segment, the previous segment's hand-off otherwise
                 uint32_t r[32];
+                const int chain = U_CHAIN, seg = U_SEG;
                 const float* s0 = p.initial_state ? p.initial_state + (int64_t)chain * 64 * V + vcol : nullptr;
+                if (seg != 0) {
+                    if (stid == 0) {
+                        const int* flag = xsync + 1 + chain * 2 + hh;
+                        uint32_t polls = 0;
+                        while (ld_acquire_gpu(flag) < seg) {
+                            __nanosleep(256);
+                            if (++polls > (1u << 25)) __trap();      // ~10 s: the predecessor died
+                        }
+                    }
+                    named_bar_sync(bar_id, 128);
+                    s0 = xstate + (int64_t)chain * 64 * V + vcol;
+                }
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = s0 ? __float_as_uint(__ldg(s0 + (int64_t)(half * 32 + j) * V)) : 0u;
+                    for (int j = 0; j < 32; ++j) r[j] = s0 ? __float_as_uint(__ldcg(s0 + (int64_t)(half * 32 + j) * V)) : 0u;
                     tmem_st32(lane_addr + kColS + hh * 64 + half * 32, r);
                 }
                 tmem_wait_st();
@@ -553,8 +597,8 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 fence_proxy_async_smem();
                 named_bar_sync(bar_id, 128);
                 if (stid == 0) {
-                    const int f = div_cpf.div(m), c0 = (m - f * cpf) << 6;
-                    tma_store_5d(&mo, smem + kOffOst + hh * 16384, 0, c0, h * VB + hh * 2, f, b);
+                    const int mg = U_NB + m, f = div_cpf.div(mg), c0 = (mg - f * cpf) << 6;
+                    tma_store_5d(&mo, smem + kOffOst + hh * 16384, 0, c0, U_HEAD * VB + hh * 2, f, U_CLIP);
                     tma_store_commit();
                 }
             };
@@ -576,7 +620,6 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             // n+1 under the state update MMA.
             wt_operand(0);
             for (int n = 0; n < NC; ++n) {
-                const int st = n & 1;
                 if (n >= 1) mbar_wait_inl(&bars[kSReady + hh], (uint32_t)(n - 1) & 1u);
                 tc_fence_after_sync();
                 PT(17, tid == 256, n);   // wait: state update of chunk n-1
@@ -634,22 +677,19 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 }
                 tc_fence_before_sync();
                 mbar_arrive(&bars[kVnbReady + hh]);
-                if (stid == 0 && n + 2 < NC) {   // U of chunk n is complete: its V half-tile slot takes chunk n + 2
-                    const int m = n + 2, f = div_cpf.div(m), c0 = (m - f * cpf) << 6;
-                    uint64_t* vb = &bars[kVTile + st * 2 + hh];
-                    mbar_arrive_expect_tx(vb, 16384u);
-                    tma_load_5d(smem + kOffV + st * kVSlotBytes + hh * 16384, &mv, vb, 0, c0, h * VB + hh * 2, f, b);
-                }
                 PT(21, tid == 256, n);   // Vnb pass
                 if (n + 1 < NC) wt_operand(n + 1);
             }
             readout(NC - 1);
             mbar_wait_inl(&bars[kSReady + hh], (uint32_t)(NC - 1) & 1u);
             tc_fence_after_sync();
-            if (p.final_state != nullptr) {
+            const int chain = U_CHAIN, seg = U_SEG;
+            const bool last_seg = seg == nseg - 1;
+            float* sT = last_seg ? p.final_state : xstate;       // the caller's final state | hand-off to the next segment
+            if (sT != nullptr) {
                 uint32_t r[32];
                 const float post = sPost[(NC - 1) & 3];
-                float* sT = p.final_state + (int64_t)chain * 64 * V + vcol;
+                sT += (int64_t)chain * 64 * V + vcol;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
                     tmem_ld32(lane_addr + kColS + hh * 64 + half * 32, r);
@@ -657,6 +697,11 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 32; ++j) sT[(int64_t)(half * 32 + j) * V] = __uint_as_float(r[j]) * post;
                 }
+            }
+            if (!last_seg) {                                     // publish: state writes of the 128 threads, then the flag
+                __threadfence();
+                named_bar_sync(bar_id, 128);
+                if (stid == 0) st_release_gpu(xsync + 1 + chain * 2 + hh, seg + 1);
             }
             if (stid == 0) tma_store_wait_all0();
             tc_fence_before_sync();
@@ -666,8 +711,9 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         // issuer K: TMA loads (one chunk of prefetch) + the [K;Q]K^T MMA
         // =========================================================================================
         {
+            const int b = U_CLIP, h = U_HEAD, nb = U_NB;
             auto issue_kq = [&](int m) {         // one elected lane arms the barrier and issues the K and Q tile loads
-                const int slot = m % 3, f = div_cpf.div(m), c0 = (m - f * cpf) << 6;
+                const int slot = m % 3, mg = nb + m, f = div_cpf.div(mg), c0 = (mg - f * cpf) << 6;
                 uint8_t* sp = smem + kOffKq + (uint32_t)slot * kKqSlotBytes;
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&bars[kKqTile + slot], 16384u);
@@ -679,7 +725,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             for (int m = 0; m < 2 && m < NC; ++m) {      // prologue: chunks 0 and 1 (their V tiles too)
                 issue_kq(m);
                 if (elect_one()) {
-                    const int f = div_cpf.div(m), c0 = (m - f * cpf) << 6;
+                    const int mg = nb + m, f = div_cpf.div(mg), c0 = (mg - f * cpf) << 6;
                     for (int hh = 0; hh < NH; ++hh) {
                         uint64_t* vb = &bars[kVTile + m * 2 + hh];
                         mbar_arrive_expect_tx(vb, 16384u);
@@ -711,6 +757,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         // =========================================================================================
         const int hh = warp - 17;
         if (hh < NH) {
+            const int b = U_CLIP, hv = U_HEAD * VB + hh * 2, nb = U_NB;
             PT_DECL
 #pragma unroll 1
             for (int n = 0; n < NC; ++n) {
@@ -749,6 +796,15 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 umma4_ts(tO, tVn, dPp, 2, kIdKK, true);                                              // O^T += Vnb P^T
                 umma_commit_w(&bars[kOFull + hh]);
                 umma_commit_w(&bars[kKsideEmpty + st]);                                              // one of NH arrivals
+                if (n + 2 < NC) {   // U of chunk n completed before Vnb was published: its V half-tile slot takes chunk n + 2
+                    if (elect_one()) {
+                        const int m = nb + n + 2, f = div_cpf.div(m), c0 = (m - f * cpf) << 6;
+                        uint64_t* vb = &bars[kVTile + st * 2 + hh];
+                        mbar_arrive_expect_tx(vb, 16384u);
+                        tma_load_5d(smem + kOffV + st * kVSlotBytes + hh * 16384, &mv, vb, 0, c0, hv, f, b);
+                    }
+                    __syncwarp();
+                }
                 PT(37, lane == 0 && hh == 0, n);   // issuer S: wait Vnb, issue state update + intra-chunk readout
             }
         }
@@ -762,6 +818,74 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
 }
 
 bool mult16(int64_t elems) { return (elems * 2) % 16 == 0; }
+
+// Number of time segments per chain: list-schedule the units (ticket order, one unit per SM at a time, a unit
+// occupies its SM while it waits for its predecessor) for every candidate count and keep the shortest makespan.
+// Unit cost = its chunks + kUnitOverhead chunk periods of set-up, pipeline fill and drain.
+constexpr double kUnitOverhead = 2.5;
+constexpr int kMaxSegments = 8;
+
+double simulate_units(int chains, int nc, int sms, int seg_chunks) {
+    const int nseg = (nc + seg_chunks - 1) / seg_chunks;
+    std::priority_queue<double, std::vector<double>, std::greater<double>> sm_free;
+    for (int i = 0; i < sms; ++i) sm_free.push(0.0);
+    std::vector<double> done((size_t)chains, 0.0);
+    double makespan = 0.0;
+    for (int s = 0; s < nseg; ++s) {
+        const double len = (double)std::min(seg_chunks, nc - s * seg_chunks) + kUnitOverhead;
+        for (int c = 0; c < chains; ++c) {
+            const double t0 = sm_free.top();
+            sm_free.pop();
+            const double end = std::max(t0, done[(size_t)c]) + len;
+            done[(size_t)c] = end;
+            sm_free.push(end);
+            makespan = std::max(makespan, end);
+        }
+    }
+    return makespan;
+}
+
+int pick_segments(int chains, int nc, int sms) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int>, int> cache;
+    const auto key = std::make_tuple(chains, nc, sms);
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    int best = 1;
+    double best_t = simulate_units(chains, nc, sms, nc);
+    if ((int64_t)chains * kMaxSegments <= (1 << 16)) {          // keep the one-off simulation cheap
+        for (int s = 2; s <= kMaxSegments && s <= nc / 8; ++s) {   // at least 8 chunks per segment
+            const int sc = (nc + s - 1) / s;
+            const double t = simulate_units(chains, nc, sms, sc);
+            if (t < best_t * 0.98) { best_t = t; best = (nc + sc - 1) / sc; }   // cut only for a real gain
+        }
+    }
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = best;
+    return best;
+}
+
+int device_sm_count() {
+    static std::mutex mu;
+    static int cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    std::lock_guard<std::mutex> lk(mu);
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+        // keep the stream-ordered pool's blocks across synchronisations (the hand-off scratch is re-used every launch)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+    }
+    return cached[dev];
+}
 
 }  // namespace
 
@@ -798,6 +922,17 @@ bool chunked_supports(const GdkvmGdrParams& p) {
     if (p.v_stride[2] != p.V || p.o_stride[2] != p.V) return false;
     if (p.q_stride[1] <= 0 || p.k_stride[1] <= 0 || p.v_stride[1] <= 0 || p.o_stride[1] <= 0) return false;
     return true;
+}
+
+int chunked_segments(const GdkvmGdrParams& p, int sms) {
+    const bool flat = p.frame_tokens <= 0 || (p.flags & GDKVM_FLAG_FLAT_CHUNKS) ||
+                      (p.frame_tokens % 64 != 0 && !(p.flags & GDKVM_FLAG_FRAME_CHUNKS));
+    const int C = flat ? p.T : p.frame_tokens, nc = (p.T / C) * ((C + 63) / 64), chains = p.B * p.H;
+    int nseg = (int)((p.flags >> 8) & 0xfu);
+    if (nseg == 0) nseg = pick_segments(chains, nc, sms > 0 ? sms : 148);
+    nseg = std::max(1, std::min(nseg, nc));
+    const int seg_chunks = (nc + nseg - 1) / nseg;
+    return (nc + seg_chunks - 1) / seg_chunks;                     // no empty segment
 }
 
 int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
@@ -840,9 +975,34 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
         if (rc == 0) rc = make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.o, dims, so, boxo, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc != 0) return (int)cudaErrorInvalidValue;
     }
-    gdr_chunk_kernel<<<p.B * p.H, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, C, F, FastDiv::make((unsigned)((C + 63) / 64)));
+    // time segments (see the header comment): explicit count in flags bits 8-11, else the simulated optimum; a launch
+    // under stream capture stays uncut (no workspace allocation inside a graph)
+    const int chains = p.B * p.H, cpf = (C + 63) / 64, nc = F * cpf;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
+    int nseg = cap != cudaStreamCaptureStatusNone ? 1 : chunked_segments(p, device_sm_count());
+    int seg_chunks = (nc + nseg - 1) / nseg;
+    float* xstate = nullptr;
+    int* xsync = nullptr;
+    void* ws = nullptr;
+    if (nseg > 1) {
+        const size_t state_bytes = (size_t)chains * 64 * V * sizeof(float), sync_bytes = ((size_t)chains * 2 + 1) * sizeof(int);
+        if (cudaMallocAsync(&ws, state_bytes + sync_bytes, stream) != cudaSuccess) {
+            (void)cudaGetLastError();
+            ws = nullptr; nseg = 1; seg_chunks = nc;                // same kernel, uncut chains
+        } else {
+            xstate = reinterpret_cast<float*>(ws);
+            xsync = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + state_bytes);
+            const cudaError_t me = cudaMemsetAsync(xsync, 0, sync_bytes, stream);
+            if (me != cudaSuccess) { cudaFreeAsync(ws, stream); return (int)me; }
+        }
+    }
+    gdr_chunk_kernel<<<chains * nseg, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, C, F, FastDiv::make((unsigned)cpf),
+                                                                      nseg, seg_chunks, xstate, xsync);
     count_launch();
-    return (int)cudaGetLastError();
+    const cudaError_t le = cudaGetLastError();
+    if (ws != nullptr) cudaFreeAsync(ws, stream);
+    return (int)le;
 }
 
 }  // namespace gdkvm

@@ -15,6 +15,8 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream);
 int launch_l2norm(const void* x, void* y, int64_t rows, int D, int64_t xs, int64_t ys, int dtype, float eps, cudaStream_t stream);
 // Host-side eligibility test of the chunked tcgen05 kernel (no GPU needed).
 bool chunked_supports(const GdkvmGdrParams& p);
+// Time segments per chain the chunked kernel would use on a device with `sms` SMs (host-side schedule simulation).
+int chunked_segments(const GdkvmGdrParams& p, int sms);
 
 void count_launch();
 

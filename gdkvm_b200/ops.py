@@ -204,5 +204,16 @@ def plan(q, k, v, g, beta, *, frame_tokens: int = 0, flags: int = 0) -> int:
     return rc
 
 
+def plan_segments(q, k, v, g, beta, *, frame_tokens: int = 0, flags: int = 0, sm_count: int = 0) -> int:
+    """Time segments per (clip, head) chain the chunked kernel would use on a device with ``sm_count`` SMs
+    (0 = 148, a B200); host arithmetic only."""
+    _check(q, k, v, g, beta, None)
+    p = _make_params(q, k, v, g, beta, v, None, None, 1.0, frame_tokens, flags)
+    rc = _cabi.load().gdkvm_gdr_plan_segments(ctypes.byref(p), int(sm_count))
+    if rc < 0:
+        raise RuntimeError(f"gdkvm_gdr_plan_segments: {_cabi.strerror(rc)}")
+    return rc
+
+
 def launch_count() -> int:
     return _cabi.launch_count()

@@ -53,6 +53,12 @@ enum GdkvmStatus {
                                            frame_tokens is a multiple of 64, flat tiling otherwise --
                                            token-causal semantics make the two exactly equivalent     */
 
+#define GDKVM_FLAG_SEGMENTS(n) (((uint32_t)(n) & 0xfu) << 8)
+                                        /* chunked kernel: cut every chain into n (1..15) time
+                                           segments scheduled as separate work units (fills the
+                                           ragged last wave of chains over SMs; bit-identical
+                                           results).  0 = let the library choose                      */
+
 /*
  * One forward call of the memory module over a batch of clips.
  *   replaces: "Linear Key-Value Association ... state transition matrix; Gated Delta Rule ...
@@ -112,6 +118,14 @@ int gdkvm_gdr_fwd(const GdkvmGdrParams* params, void* cuda_stream);
  * Needs no GPU.
  */
 int gdkvm_gdr_plan(const GdkvmGdrParams* params);
+
+/*
+ * Time segments per chain gdkvm_gdr_fwd would cut the problem into on a device with `sm_count` SMs (<= 0: 148, a B200):
+ * 1 = one work unit per (clip, head) chain; n > 1 = n units per chain, scheduled in order, so that the last wave of
+ * units over the SMs is not ragged (GDKVM_FLAG_SEGMENTS overrides; launches under stream capture are never cut).
+ * Pure host arithmetic, needs no GPU.  Returns 1 for the recurrent path, negative = GdkvmStatus.
+ */
+int gdkvm_gdr_plan_segments(const GdkvmGdrParams* params, int sm_count);
 
 /*
  * Row-wise L2 normalisation  y[r][:] = x[r][:] * rsqrt(sum(x[r][:]^2) + eps)  of `rows` rows of D elements (dtype:

@@ -78,6 +78,31 @@ def test_plan_and_validation(built_lib):
     assert "unknown" in _cabi.strerror(-99)
 
 
+def test_time_segment_planning(built_lib):
+    """Host-side schedule simulation behind gdkvm_gdr_plan_segments: chains are cut in time only when the last wave of
+    (clip, head) chains over the SMs is ragged, never into segments shorter than 8 chunks, and a forced count wins."""
+    import gdkvm_b200 as G
+
+    def segs(B, F, C, H, V=256, flags=0, sms=0):
+        T = F * C
+        q = torch.empty(B, T, H, 64, dtype=torch.bfloat16)
+        v = torch.empty(B, T, H, V, dtype=torch.bfloat16)
+        g = torch.empty(B, T, H)
+        return G.plan_segments(q, q, v, g, g, frame_tokens=C, flags=flags, sm_count=sms)
+
+    assert segs(64, 128, 49, 8) == 2            # configs[1]: 512 chains on 148 SMs = 3.46 waves -> 1024 units, 6.92 waves
+    assert segs(32, 20, 1024, 8) == 4           # configs[2] shape: 256 chains = 1.73 waves
+    assert segs(8, 128, 49, 8) == 1             # 64 chains < 148 SMs: nothing to balance
+    assert segs(37, 100, 64, 4) == 1            # exactly one wave
+    assert segs(64, 128, 49, 8, sms=128) == 1   # 512 chains on 128 SMs: four full waves
+    assert segs(3, 9, 64, 2) == 1               # short chains stay whole (< 8 chunks per segment)
+    assert segs(64, 128, 49, 8, flags=G.FLAG_SEGMENTS(5)) == 5
+    assert segs(1, 3, 64, 1, flags=G.FLAG_SEGMENTS(15)) == 3      # at most one segment per chunk
+    assert segs(2, 10, 64, 1, flags=G.FLAG_SEGMENTS(4)) == 4      # 10 chunks in 3+3+3+1
+    assert segs(2, 10, 64, 1, flags=G.FLAG_SEGMENTS(6)) == 5      # 2 chunks per segment -> 5 segments, none empty
+    assert segs(2, 40, 49, 2, V=40, flags=1) == 1                 # recurrent path: no segments
+
+
 def test_fwd_without_gpu_fails_loudly(built_lib):
     """No GPU here: the C entry point must return an error, never compute on the host."""
     if torch.cuda.is_available():

@@ -264,6 +264,48 @@ def test_host_pipeline_matches_device_call(op):
 
 # ---------------- full-size (BASELINE configs[1]) properties ----------------
 
+def SEG(n):
+    return (n & 0xF) << 8
+
+
+@pytest.mark.parametrize("shape", [
+    # B, T, H, V, frame_tokens, flags
+    (3, 9 * 64 + 17, 2, 256, 0, 0),            # flat tiling, ragged tail in the last segment
+    (2, 7 * 49, 3, 256, 49, FRAME),            # one padded chunk per frame
+    (2, 3 * 128, 2, 128, 128, 0),              # V = 128 (one state warpgroup), 2 sub-chunks per frame
+    (40, 6 * 64, 8, 256, 0, 0),                # 320 chains x up to 6 segments: several waves of units, real waiting
+])
+def test_time_segments_are_bit_identical(op, shape):
+    """Chains cut into time segments (separate work units, fp32 state handed over through global memory) give
+    exactly the bits of the uncut chains: readout, final state, with and without an initial state."""
+    B, T, H, V, C, fl = shape
+    q, k, v, g, beta, S0 = _dev(*make_inputs(B, T, H, 64, V, seed=41, frame_tokens=C, dtype=torch.bfloat16))
+    for s0 in (S0, None):
+        o1, s1 = op.gdr_lkva(q, k, v, g, beta, None, s0, True, C, CHUNKED | fl | SEG(1))
+        for n in (2, 3, 5, 15):
+            o, sT = op.gdr_lkva(q, k, v, g, beta, None, s0, True, C, CHUNKED | fl | SEG(n))
+            assert torch.equal(o, o1) and torch.equal(sT, s1), (n, s0 is None)
+    o1, _ = op.gdr_lkva(q, k, v, g, beta, None, S0, True, C, CHUNKED | fl | SEG(1))
+    o, _ = op.gdr_lkva(q, k, v, g, beta, None, S0, False, C, CHUNKED | fl | SEG(4))     # no final state requested
+    assert torch.equal(o, o1)
+    if B <= 3:
+        qc, kc, vc, gc, bc, sc = (t.cpu() for t in (q, k, v, g, beta, S0))
+        o_ref, s_ref = gdr_recurrent_ref(qc, kc, vc, gc, bc, None, sc)
+        o, sT = op.gdr_lkva(q, k, v, g, beta, None, S0, True, C, CHUNKED | fl | SEG(3))
+        assert max_rel_err(o, o_ref) <= 2e-2 and max_rel_err(sT, s_ref) <= 2e-2
+
+
+def test_time_segments_with_slow_path_chunks(op):
+    q, k, v, g, beta, S0 = make_inputs(2, 6 * 64, 2, 64, 256, seed=42, dtype=torch.bfloat16)
+    g = g.clone()
+    g[:, 64:256] *= 300.0
+    q, k, v, g, beta, S0 = _dev(q, k, v, g, beta, S0)
+    o1, s1 = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 0, CHUNKED | SEG(1))
+    for n in (2, 3, 6):
+        o, sT = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 0, CHUNKED | SEG(n))
+        assert torch.equal(o, o1) and torch.equal(sT, s1), n
+
+
 @pytest.fixture(scope="module")
 def echonet_batch():
     """configs[1]: 64 clips x 128 frames x 49 tokens, 8 heads, K=64, V=256, bf16 -- built on the GPU."""
@@ -308,6 +350,15 @@ def test_full_size_state_carry(op, echonet_batch):
     oa, sa = op.gdr_lkva(q[:, :cut], k[:, :cut], v[:, :cut], g[:, :cut], beta[:, :cut], None, S0, True, 49)
     ob, sb = op.gdr_lkva(q[:, cut:], k[:, cut:], v[:, cut:], g[:, cut:], beta[:, cut:], None, sa, True, 49)
     assert torch.equal(oa, o[:, :cut]) and torch.equal(ob, o[:, cut:]) and torch.equal(sb, sT)
+
+
+def test_full_size_segments_agree(op, echonet_batch):
+    """configs[1]: the library's own choice of time segments vs uncut chains vs 4 segments, bit for bit."""
+    q, k, v, g, beta, S0 = echonet_batch
+    o, sT = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 49)
+    for n in (1, 4):
+        o_n, s_n = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 49, SEG(n))
+        assert torch.equal(o_n, o) and torch.equal(s_n, sT), n
 
 
 def test_full_size_paths_agree(op, echonet_batch):
