@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--varlen", type=float, default=0.0,
+                    help="s > 0: pack the batch and cut it into clips of lengths uniform in [1-s, 1+s] x frames (cu_seqlens call)")
     ap.add_argument("--flags", type=int, default=0, help="GDKVM_FLAG_* forwarded to the op (1=recurrent, 2=chunked, 4=flat, 8=frame chunks, n<<8 = n time segments)")
     ap.add_argument("--workload", default="echonet_batch", choices=sorted(WORKLOADS),
                     help="echonet_batch = BASELINE configs[1] (the bench line); camus / long_clip = configs[2] / [3] shapes per GPU")
@@ -217,8 +219,26 @@ def main():
     o = torch.empty(B, T, H, V, dtype=torch.bfloat16, device=dev)
     sT = torch.empty(B, H, K, V, dtype=torch.float32, device=dev)
 
+    varlen = None
+    if args.varlen > 0:
+        # the same tokens as the fixed-length batch, packed, cut into B clips of different lengths (whole frames,
+        # uniform in [1 - s, 1 + s] x frames): the `cu_seqlens` entry point; extra line, not the contract workload
+        gen = torch.Generator().manual_seed(4321 + rank)
+        w = 1.0 + args.varlen * (2.0 * torch.rand(B, generator=gen) - 1.0)
+        fr = torch.clamp((w / w.sum() * B * W["frames"]).round().long(), min=1)
+        fr[-1] += B * W["frames"] - int(fr.sum())
+        assert int(fr.min()) >= 1
+        cu = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(fr * C, 0)]).to(dev)
+        pk = lambda t: t.reshape(1, B * T, *t.shape[2:])
+        varlen = dict(q=pk(q), k=pk(k), v=pk(v), g=pk(g), beta=pk(beta), cu=cu, frames=[int(x) for x in fr])
+        args.no_e2e = args.no_cpu = True
+
     def step():
-        gdkvm_b200.gdr_lkva_out(q, k, v, g, beta, o, sT, None, S0, C, args.flags)
+        if varlen is not None:
+            gdkvm_b200.gdr_lkva_varlen(varlen["q"], varlen["k"], varlen["v"], varlen["g"], varlen["beta"], varlen["cu"],
+                                       None, S0, True, args.flags)
+        else:
+            gdkvm_b200.gdr_lkva_out(q, k, v, g, beta, o, sT, None, S0, C, args.flags)
 
     def barrier():
         torch.cuda.synchronize()
@@ -270,7 +290,7 @@ def main():
     if not args.no_e2e:
         pin = lambda t: t.cpu().pin_memory()
         hq, hk, hv, hg, hb, hs = map(pin, (q, k, v, g, beta, S0))
-        pipe = HostPipeline(B, T, H, K, V, torch.bfloat16, torch.float32, clips_per_group=8, device=dev)
+        pipe = HostPipeline(B, T, H, K, V, torch.bfloat16, torch.float32, clips_per_group=2, device=dev)
         ho, hsT = pipe.alloc_host_outputs()
         e2e_steps = max(1, min(args.steps, 5))
         for _ in range(2):
@@ -361,6 +381,8 @@ def main():
                    "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % (abytes / 1e9),
                    "sharding": "clips x heads across ranks, no collective on the hot path"},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+        **({"varlen": {"spread": args.varlen, "min_frames": min(varlen["frames"]), "max_frames": max(varlen["frames"]),
+                       "entry": "gdkvm_gdr_fwd_varlen (cu_seqlens on the device)"}} if varlen is not None else {}),
         "clocks": clocks,
     }
     if gather_ms is not None:

@@ -19,7 +19,7 @@ def FLAG_SEGMENTS(n: int) -> int:
 
 EXPORTED_SYMBOLS = (
     "gdkvm_abi_version", "gdkvm_strerror", "gdkvm_last_cuda_error",
-    "gdkvm_gdr_fwd", "gdkvm_gdr_plan", "gdkvm_gdr_plan_segments", "gdkvm_launch_count", "gdkvm_l2norm_fwd",
+    "gdkvm_gdr_fwd", "gdkvm_gdr_fwd_varlen", "gdkvm_gdr_plan", "gdkvm_gdr_plan_segments", "gdkvm_launch_count", "gdkvm_l2norm_fwd",
 )
 
 
@@ -59,6 +59,9 @@ def load() -> ctypes.CDLL:
             lib.gdkvm_last_cuda_error.restype = ctypes.c_int
             lib.gdkvm_gdr_fwd.restype = ctypes.c_int
             lib.gdkvm_gdr_fwd.argtypes = [ctypes.POINTER(GdkvmGdrParams), ctypes.c_void_p]
+            lib.gdkvm_gdr_fwd_varlen.restype = ctypes.c_int
+            lib.gdkvm_gdr_fwd_varlen.argtypes = [ctypes.POINTER(GdkvmGdrParams), ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                                 ctypes.c_void_p]
             lib.gdkvm_gdr_plan.restype = ctypes.c_int
             lib.gdkvm_gdr_plan.argtypes = [ctypes.POINTER(GdkvmGdrParams)]
             lib.gdkvm_gdr_plan_segments.restype = ctypes.c_int

@@ -126,6 +126,28 @@ int gdkvm_l2norm_fwd(const void* x, void* y, int64_t rows, int32_t D, int64_t x_
     return GDKVM_OK;
 }
 
+int gdkvm_gdr_fwd_varlen(const GdkvmGdrParams* params, const void* cu_seqlens, int32_t cu_seqlens_bytes, int32_t n_seqs,
+                         void* cuda_stream) {
+    int rc = gdkvm::validate(params);
+    if (rc != GDKVM_OK) return rc;
+    if (params->B != 1 || n_seqs < 1 || (cu_seqlens_bytes != 4 && cu_seqlens_bytes != 8)) return GDKVM_ERR_SHAPE;
+    if (cu_seqlens == nullptr) return GDKVM_ERR_NULL;
+    if (reinterpret_cast<uintptr_t>(cu_seqlens) % (uintptr_t)cu_seqlens_bytes != 0) return GDKVM_ERR_ALIGN;
+    if ((int64_t)n_seqs * params->H > 0x3fffffff) return GDKVM_ERR_SHAPE;
+    const int path = gdkvm::pick(params);
+    if (path < 0) return path;
+    bool sm100 = false;
+    int ce = gdkvm::device_is_sm100(&sm100);
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    if (!sm100) return GDKVM_ERR_ARCH;
+    if (params->T == 0) return GDKVM_OK;
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    ce = path == 1 ? gdkvm::launch_chunked_varlen(*params, cu_seqlens, cu_seqlens_bytes, n_seqs, stream)
+                   : gdkvm::launch_recurrent_varlen(*params, cu_seqlens, cu_seqlens_bytes, n_seqs, stream);
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    return GDKVM_OK;
+}
+
 int gdkvm_gdr_fwd(const GdkvmGdrParams* params, void* cuda_stream) {
     int rc = gdkvm::validate(params);
     if (rc != GDKVM_OK) return rc;

@@ -42,6 +42,13 @@
 // (64 KiB per chain, released by a flag); the arithmetic is the one of an uncut chain, bit for bit.  The host picks
 // nseg by simulating the unit schedule (pick_segments).
 //
+// Packed variable-length sequences (kVar, the `cu_seqlens` call): the clips lie back to back in one token stream.  A
+// one-block prologue kernel turns the device-resident sequence offsets into a table of work units (sequence, first
+// token, valid tokens, chunks, segment), level by level so that every unit's predecessor comes earlier in ticket
+// order; the host only knows an upper bound of the unit count and the surplus CTAs leave at once.  Rows past the end
+// of a sequence carry the NEXT sequence's tokens: g = beta = 0 makes them exact no-ops of the recurrence, and the
+// last chunk's readout is stored row by row instead of by TMA so that nothing is written past the sequence.
+//
 // Layout facts used here were verified on hardware by tests/probes/umma_probe.cu.
 // Math: oracle/gdr_ref.py::gdr_chunk_ref.
 #include <algorithm>
@@ -82,7 +89,7 @@ constexpr uint32_t kOffF = kOffH + 8192;
 constexpr uint32_t kNumFloats = 18 * 64 + 12;
 constexpr uint32_t kOffBar = kOffF + kNumFloats * 4;
 constexpr uint32_t kNumBars = 27;
-constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 32 + 1024;   // + tmem slot + unit info + alignment slack
+constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 48 + 1024;   // + tmem slot + unit info + alignment slack
 static_assert(kSmemBytes <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
 // ---- tensor memory map (columns) ----
@@ -251,12 +258,21 @@ __device__ __forceinline__ void w_unit_mma(uint32_t aK, uint32_t aT, uint8_t* wt
 // four 128x64x16 tcgen05 MMAs covering K = 64; descriptors advance by a fixed step per K slice.
 // Warp-uniform: called by every lane of the (converged) issuer warp, one elected lane issues.
 __device__ __forceinline__ void umma4_ss(uint32_t d, uint64_t a, uint32_t astep, uint64_t bdesc, uint32_t bstep, uint32_t idesc, bool acc0) {
+#ifdef GDKVM_UMMA_SINGLE
 #pragma unroll
     for (int k = 0; k < 4; ++k) umma_ss_w(d, a + (uint64_t)(k * astep), bdesc + (uint64_t)(k * bstep), idesc, acc0 || k > 0);
+#else
+    umma4_ss_w(d, a, a + (uint64_t)astep, a + (uint64_t)(2 * astep), a + (uint64_t)(3 * astep), bdesc, bdesc + (uint64_t)bstep,
+               bdesc + (uint64_t)(2 * bstep), bdesc + (uint64_t)(3 * bstep), idesc, acc0);
+#endif
 }
 __device__ __forceinline__ void umma4_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t bstep, uint32_t idesc, bool acc0) {
+#ifdef GDKVM_UMMA_SINGLE
 #pragma unroll
     for (int k = 0; k < 4; ++k) umma_ts_w(d, a_tmem + k * 8, bdesc + (uint64_t)(k * bstep), idesc, acc0 || k > 0);
+#else
+    umma4_ts_w(d, a_tmem, bdesc, bdesc + (uint64_t)bstep, bdesc + (uint64_t)(2 * bstep), bdesc + (uint64_t)(3 * bstep), idesc, acc0);
+#endif
 }
 
 // n / d for 0 <= n < 2^31 and a run-time d >= 1 without the ~40-instruction integer division sequence (the kernel is
@@ -277,11 +293,17 @@ struct FastDiv {
     __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((unsigned int)n, mul) >> shr); }
 };
 
+// work-unit table of the packed variable-length call: utab[0] = number of entries, entry e at utab + 8 + 8 e:
+// [0] sequence [1] first token (row of the packed stream) [2] valid tokens [3] chunks [4] segment [5] last segment
+constexpr int kUnitInts = 8;
+
+template <bool kVar>
 __global__ void __launch_bounds__(kThreads, 1)
 gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                  const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mo,
                  const GdkvmGdrParams p, const int C, const int F, const FastDiv div_cpf,
-                 const int nseg, const int seg_chunks, float* __restrict__ xstate, int* __restrict__ xsync) {
+                 const int nseg, const int seg_chunks, float* __restrict__ xstate, int* __restrict__ xsync,
+                 const int* __restrict__ utab) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-align inside the shared window with pointer arithmetic only (an integer round trip would
     // demote every access below from LDS/STS to generic LD/ST)
@@ -298,8 +320,8 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     float* sFast = sPre + 4;                              // [4] chunk n in slot n & 3
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
-    // work unit of this CTA, written once by thread 0: [0] time segment [1] chain [2] clip [3] head [4] first chunk.
-    // Read through a volatile pointer where it is used (single threads, outside the hot loops) so that
+    // work unit of this CTA, written once by thread 0: [0] time segment [1] chain [2] clip [3] head [4] first chunk
+    // (kVar: first token) [5] kVar: chunks [6] kVar: valid tokens [7] last segment of the chain.  Read through a volatile pointer where it is used (single threads, outside the hot loops) so that
     // none of it occupies registers of the instruction-bound warps for the whole kernel.
     volatile int* s_info = reinterpret_cast<volatile int*>(s_tmem + 1);
 
@@ -308,12 +330,26 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     const int cpf = (C + 63) >> 6;
     const float scale = p.scale;
 
+    if constexpr (kVar) {
+        if (tid == 0) {       // unit = ticket -> (table entry, head); CTAs past the end of the table have nothing to do
+            const int unit = atomicAdd(xsync, 1), entry = unit / p.H, head = unit - entry * p.H;
+            s_info[5] = 0;
+            if (entry < utab[0]) {
+                const int* e = utab + kUnitInts * (1 + entry);
+                s_info[0] = e[4]; s_info[1] = e[0] * p.H + head; s_info[2] = 0; s_info[3] = head;
+                s_info[4] = e[1]; s_info[5] = e[3]; s_info[6] = e[2]; s_info[7] = e[5];
+            }
+        }
+        __syncthreads();
+        if (s_info[5] == 0) return;
+    }
     if (tid == 0) {
-        // unit -> (time segment, chain), in ticket order when chains are cut in time
-                const int unit = nseg > 1 ? atomicAdd(xsync, 1) : (int)blockIdx.x, nchains = p.B * p.H;
-        const int seg = unit / nchains, chain = unit - seg * nchains, clip = chain / p.H, nb = seg * seg_chunks;
-        s_info[0] = seg; s_info[1] = chain; s_info[2] = clip; s_info[3] = chain - clip * p.H;
-        s_info[4] = nb;
+        if constexpr (!kVar) {    // unit -> (time segment, chain), in ticket order when chains are cut in time
+            const int unit = nseg > 1 ? atomicAdd(xsync, 1) : (int)blockIdx.x, nchains = p.B * p.H;
+            const int seg = unit / nchains, chain = unit - seg * nchains, clip = chain / p.H, nb = seg * seg_chunks;
+            s_info[0] = seg; s_info[1] = chain; s_info[2] = clip; s_info[3] = chain - clip * p.H;
+            s_info[4] = nb; s_info[7] = seg == nseg - 1;
+        }
         for (int i = 0; i < 3; ++i) mbar_init(&bars[kKqTile + i], 1);
         for (int i = 0; i < 4; ++i) mbar_init(&bars[kVTile + i], 1);
         mbar_init(&bars[kKqFull], 1); mbar_init(&bars[kKqFree], kKThreads);
@@ -344,7 +380,13 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     // Chunks s_info[4] .. + NC - 1 of the chain; n below counts inside the segment.  NC is the same for every unit (a
     // kernel parameter, so every loop bound stays warp-uniform for the compiler); chunks past the end of the chain in
     // the last segment are exact no-ops: tiles zero-filled by TMA, gates 0, stores clipped.
-    const int NC = seg_chunks, nc_chain = F * cpf;
+    // (kVar: per unit, from the table.)
+    const int NC = kVar ? (int)s_info[5] : seg_chunks, nc_chain = F * cpf;
+    // chunk n of this unit -> tensor-map coordinates (token in frame, frame)
+    auto chunk_coord = [&](int n, int& c0, int& f) {
+        if constexpr (kVar) { f = 0; c0 = s_info[4] + (n << 6); }
+        else { const int m = s_info[4] + n; f = div_cpf.div(m); c0 = (m - f * cpf) << 6; }
+    };
 #define U_SEG s_info[0]
 #define U_CHAIN s_info[1]
 #define U_CLIP s_info[2]
@@ -370,13 +412,14 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         const int64_t g_off = (int64_t)U_CLIP * p.g_stride[0] + (int64_t)U_HEAD * p.g_stride[2];
         const int64_t bt_off = (int64_t)U_CLIP * p.beta_stride[0] + (int64_t)U_HEAD * p.beta_stride[2];
         auto load_gates = [&](int n, float (&gv)[2], float (&bv)[2]) {
-            const int m = U_NB + n, f = div_cpf.div(m);
+            const int m = U_NB + n, f = kVar ? 0 : div_cpf.div(m);
+            const int ntok = kVar ? (int)s_info[6] : 0;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int c = ((m - f * cpf) << 6) + 2 * lane + e;
+                const int c = kVar ? (n << 6) + 2 * lane + e : ((m - f * cpf) << 6) + 2 * lane + e;
                 gv[e] = 0.f; bv[e] = 0.f;                        // pad rows: exact no-ops
-                if (c < C && m < nc_chain) {
-                    const int64_t t = (int64_t)f * C + c;
+                if (kVar ? c < ntok : (c < C && m < nc_chain)) {
+                    const int64_t t = kVar ? (int64_t)s_info[4] + c : (int64_t)f * C + c;
                     gv[e] = load_gate(p.g, g_off + t * p.g_stride[1], p.gate_dtype);
                     bv[e] = load_gate(p.beta, bt_off + t * p.beta_stride[1], p.gate_dtype);
                 }
@@ -596,8 +639,20 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 mbar_arrive(&bars[kOFree + hh]);
                 fence_proxy_async_smem();
                 named_bar_sync(bar_id, 128);
-                if (stid == 0) {
-                    const int mg = U_NB + m, f = div_cpf.div(mg), c0 = (mg - f * cpf) << 6;
+                if (kVar && (int)s_info[6] - (m << 6) < 64) {
+                    // last chunk of a packed sequence: the rows behind it belong to the next sequence, so the valid rows
+                    // leave through ordinary 16-byte stores (staging tile: [value block][token][64], 128B swizzle)
+                    const int valid = (int)s_info[6] - (m << 6);
+                    __nv_bfloat16* og = reinterpret_cast<__nv_bfloat16*>(p.o) + ((int64_t)s_info[4] + (m << 6)) * p.o_stride[1] +
+                                        (int64_t)s_info[3] * p.o_stride[2] + hh * 128;
+                    for (int idx = stid; idx < valid * 16; idx += 128) {
+                        const int row = idx >> 4, blk = (idx >> 3) & 1, ck = idx & 7;
+                        const uint4 val = *reinterpret_cast<const uint4*>(smem + kOffOst + hh * 16384 + blk * 8192 + sw128_offset(row, ck));
+                        *reinterpret_cast<uint4*>(og + (int64_t)row * p.o_stride[1] + blk * 64 + ck * 8) = val;
+                    }
+                } else if (stid == 0) {
+                    int c0, f;
+                    chunk_coord(m, c0, f);
                     tma_store_5d(&mo, smem + kOffOst + hh * 16384, 0, c0, U_HEAD * VB + hh * 2, f, U_CLIP);
                     tma_store_commit();
                 }
@@ -684,7 +739,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             mbar_wait_inl(&bars[kSReady + hh], (uint32_t)(NC - 1) & 1u);
             tc_fence_after_sync();
             const int chain = U_CHAIN, seg = U_SEG;
-            const bool last_seg = seg == nseg - 1;
+            const bool last_seg = s_info[7] != 0;
             float* sT = last_seg ? p.final_state : xstate;       // the caller's final state | hand-off to the next segment
             if (sT != nullptr) {
                 uint32_t r[32];
@@ -711,9 +766,11 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         // issuer K: TMA loads (one chunk of prefetch) + the [K;Q]K^T MMA
         // =========================================================================================
         {
-            const int b = U_CLIP, h = U_HEAD, nb = U_NB;
+            const int b = U_CLIP, h = U_HEAD;
             auto issue_kq = [&](int m) {         // one elected lane arms the barrier and issues the K and Q tile loads
-                const int slot = m % 3, mg = nb + m, f = div_cpf.div(mg), c0 = (mg - f * cpf) << 6;
+                const int slot = m % 3;
+                int c0, f;
+                chunk_coord(m, c0, f);
                 uint8_t* sp = smem + kOffKq + (uint32_t)slot * kKqSlotBytes;
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&bars[kKqTile + slot], 16384u);
@@ -725,7 +782,8 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             for (int m = 0; m < 2 && m < NC; ++m) {      // prologue: chunks 0 and 1 (their V tiles too)
                 issue_kq(m);
                 if (elect_one()) {
-                    const int mg = nb + m, f = div_cpf.div(mg), c0 = (mg - f * cpf) << 6;
+                    int c0, f;
+                    chunk_coord(m, c0, f);
                     for (int hh = 0; hh < NH; ++hh) {
                         uint64_t* vb = &bars[kVTile + m * 2 + hh];
                         mbar_arrive_expect_tx(vb, 16384u);
@@ -757,7 +815,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         // =========================================================================================
         const int hh = warp - 17;
         if (hh < NH) {
-            const int b = U_CLIP, hv = U_HEAD * VB + hh * 2, nb = U_NB;
+            const int b = U_CLIP, hv = U_HEAD * VB + hh * 2;
             PT_DECL
 #pragma unroll 1
             for (int n = 0; n < NC; ++n) {
@@ -798,7 +856,8 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 umma_commit_w(&bars[kKsideEmpty + st]);                                              // one of NH arrivals
                 if (n + 2 < NC) {   // U of chunk n completed before Vnb was published: its V half-tile slot takes chunk n + 2
                     if (elect_one()) {
-                        const int m = nb + n + 2, f = div_cpf.div(m), c0 = (m - f * cpf) << 6;
+                        int c0, f;
+                        chunk_coord(n + 2, c0, f);
                         uint64_t* vb = &bars[kVTile + st * 2 + hh];
                         mbar_arrive_expect_tx(vb, 16384u);
                         tma_load_5d(smem + kOffV + st * kVSlotBytes + hh * 16384, &mv, vb, 0, c0, hv, f, b);
@@ -935,46 +994,131 @@ int chunked_segments(const GdkvmGdrParams& p, int sms) {
     return (nc + seg_chunks - 1) / seg_chunks;                     // no empty segment
 }
 
-int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
+namespace {
+
+// dynamic shared memory opt-in of both kernel instantiations (per device: retried until it has succeeded)
+int ensure_smem_attr() {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(gdr_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    });
-    if (attr_err != cudaSuccess) {   // per-device attribute: retry (another device may be current now)
-        attr_err = cudaFuncSetAttribute(gdr_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        if (attr_err != cudaSuccess) return (int)attr_err;
+    auto set = [] {
+        cudaError_t e = cudaFuncSetAttribute(gdr_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gdr_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        return e;
+    };
+    std::call_once(once, [&] { attr_err = set(); });
+    if (attr_err != cudaSuccess) attr_err = set();      // another device may be current now
+    return (int)attr_err;
+}
+
+// Tensor maps of q, k (dk, token-in-frame, frame, head, clip) and v, o (64 values, token-in-frame, head x value block,
+// frame, clip): C tokens per frame, F frames; one 128-column value half per v / o box (each state warpgroup loads and
+// stores its own half).
+int make_maps(const GdkvmGdrParams& p, int C, int F, CUtensorMap* mq, CUtensorMap* mk, CUtensorMap* mv, CUtensorMap* mo) {
+    const uint64_t B = p.B, H = p.H, V = p.V;
+    {
+        const uint64_t dims[5] = {64, (uint64_t)C, (uint64_t)F, H, B};
+        const uint32_t box[5] = {64, 64, 1, 1, 1};
+        const uint64_t sq[4] = {(uint64_t)p.q_stride[1] * 2, (uint64_t)p.q_stride[1] * 2 * C, (uint64_t)p.q_stride[2] * 2, (uint64_t)p.q_stride[0] * 2};
+        const uint64_t sk[4] = {(uint64_t)p.k_stride[1] * 2, (uint64_t)p.k_stride[1] * 2 * C, (uint64_t)p.k_stride[2] * 2, (uint64_t)p.k_stride[0] * 2};
+        int rc = make_tmap(mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.q, dims, sq, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc == 0) rc = make_tmap(mk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.k, dims, sk, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != 0) return (int)cudaErrorInvalidValue;
     }
+    {
+        const uint64_t dims[5] = {64, (uint64_t)C, H * (V / 64), (uint64_t)F, B};
+        const uint32_t box[5] = {64, 64, 2, 1, 1};
+        const uint64_t sv[4] = {(uint64_t)p.v_stride[1] * 2, 128, (uint64_t)p.v_stride[1] * 2 * C, (uint64_t)p.v_stride[0] * 2};
+        const uint64_t so[4] = {(uint64_t)p.o_stride[1] * 2, 128, (uint64_t)p.o_stride[1] * 2 * C, (uint64_t)p.o_stride[0] * 2};
+        int rc = make_tmap(mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.v, dims, sv, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc == 0) rc = make_tmap(mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.o, dims, so, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != 0) return (int)cudaErrorInvalidValue;
+    }
+    return 0;
+}
+
+// Work-unit table of the packed variable-length call, built on the device from the sequence offsets (one block).
+// Level l holds segment l of every sequence that has one, in sequence order; levels follow each other, so a unit's
+// predecessor (same sequence, level l - 1) always has a smaller ticket.  Sequences without tokens get no unit: their
+// final state is the initial state (copied here).
+template <typename IdxT>
+__global__ void __launch_bounds__(256) gdr_units_kernel(const IdxT* __restrict__ cu, int nseq, int seg_chunks, int max_entries,
+                                                        int* __restrict__ utab, int H, int state_elems,
+                                                        const float* __restrict__ s0, float* __restrict__ sT) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base, s_levels;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_base = 0; s_levels = 0; }
+    __syncthreads();
+    // a sequence of c chunks is cut into round(c / seg_chunks) (>= 1) segments of equal size (no short remainder unit)
+    auto chunks_of = [&](int n) {
+        const long long len = (long long)cu[n + 1] - (long long)cu[n];
+        return len > 0 ? (int)((len + 63) >> 6) : 0;
+    };
+    auto seg_size = [&](int chunks) {            // chunks per segment (chunks > 0)
+        const int want = max(1, (chunks + seg_chunks / 2) / seg_chunks);
+        return (chunks + want - 1) / want;
+    };
+    auto segs_of = [&](int n) {                  // every segment non-empty: (segs - 1) * size < chunks
+        const int chunks = chunks_of(n);
+        return chunks == 0 ? 0 : (chunks + seg_size(chunks) - 1) / seg_size(chunks);
+    };
+    int mx = 0;
+    for (int n = tid; n < nseq; n += 256) mx = max(mx, segs_of(n));
+    atomicMax(&s_levels, mx);
+    __syncthreads();
+    const int levels = s_levels;
+    for (int lvl = 0; lvl < levels; ++lvl) {
+        for (int n0 = 0; n0 < nseq; n0 += 256) {
+            const int n = n0 + tid;
+            const int nsegs = n < nseq ? segs_of(n) : 0;
+            const bool has = nsegs > lvl;
+            const unsigned m = __ballot_sync(0xffffffffu, has);
+            if (lane == 0) s_warp[warp] = __popc(m);
+            __syncthreads();
+            int pos = s_base + __popc(m & ((1u << lane) - 1u)), total = 0;
+            for (int w = 0; w < 8; ++w) { if (w < warp) pos += s_warp[w]; total += s_warp[w]; }
+            if (has && pos < max_entries) {
+                const long long t0 = (long long)cu[n], len = (long long)cu[n + 1] - t0;
+                const int sc = seg_size(chunks_of(n));                       // chunks per segment of this sequence
+                const int first = lvl * sc;                                  // first chunk of this segment
+                const long long rest = len - (long long)first * 64;         // tokens from there to the end of the sequence
+                const bool last = lvl == nsegs - 1;
+                int* e = utab + kUnitInts * (1 + pos);
+                e[0] = n; e[1] = (int)(t0 + (long long)first * 64);
+                e[2] = last ? (int)rest : sc * 64;
+                e[3] = last ? (int)((rest + 63) >> 6) : sc;
+                e[4] = lvl; e[5] = last ? 1 : 0; e[6] = 0; e[7] = 0;
+            }
+            __syncthreads();
+            if (tid == 0) s_base += total;
+            __syncthreads();
+        }
+    }
+    if (tid == 0) utab[0] = min(s_base, max_entries);
+    if (sT != nullptr) {
+        for (int n = 0; n < nseq; ++n) {
+            if ((long long)cu[n + 1] - (long long)cu[n] > 0) continue;
+            const size_t off = (size_t)n * H * state_elems;
+            for (int i = tid; i < H * state_elems; i += 256) sT[off + i] = s0 != nullptr ? s0[off + i] : 0.f;
+        }
+    }
+}
+
+}  // namespace
+
+int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
+    const int ae = ensure_smem_attr();
+    if (ae != 0) return ae;
     // frame-aligned chunks when frames are whole 64-token chunks (or when asked for); otherwise tile the
     // flat token stream: identical results (token-causal recurrence), no zero-padded rows to process
     const bool flat = p.frame_tokens <= 0 || (p.flags & GDKVM_FLAG_FLAT_CHUNKS) ||
                       (p.frame_tokens % 64 != 0 && !(p.flags & GDKVM_FLAG_FRAME_CHUNKS));
     const int C = flat ? p.T : p.frame_tokens;
     const int F = p.T / C;
-    const uint64_t B = p.B, H = p.H, V = p.V;
+    const uint64_t V = p.V;
     CUtensorMap mq, mk, mv, mo;
-    // q,k: (dk, token-in-frame, frame, head, clip)
-    {
-        const uint64_t dims[5] = {64, (uint64_t)C, (uint64_t)F, H, B};
-        const uint32_t box[5] = {64, 64, 1, 1, 1};
-        const uint64_t sq[4] = {(uint64_t)p.q_stride[1] * 2, (uint64_t)p.q_stride[1] * 2 * C, (uint64_t)p.q_stride[2] * 2, (uint64_t)p.q_stride[0] * 2};
-        const uint64_t sk[4] = {(uint64_t)p.k_stride[1] * 2, (uint64_t)p.k_stride[1] * 2 * C, (uint64_t)p.k_stride[2] * 2, (uint64_t)p.k_stride[0] * 2};
-        int rc = make_tmap(&mq, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.q, dims, sq, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc == 0) rc = make_tmap(&mk, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.k, dims, sk, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc != 0) return (int)cudaErrorInvalidValue;
-    }
-    // v, o: (64 values, token-in-frame, head x value-block, frame, clip), one 128-column half per box
-    // (each state warpgroup loads / stores its own half)
-    {
-        const uint64_t dims[5] = {64, (uint64_t)C, H * (V / 64), (uint64_t)F, B};
-        const uint32_t boxv[5] = {64, 64, 2, 1, 1};      // one 128-column value half per box (per-half ring slots)
-        const uint32_t boxo[5] = {64, 64, 2, 1, 1};
-        const uint64_t sv[4] = {(uint64_t)p.v_stride[1] * 2, 128, (uint64_t)p.v_stride[1] * 2 * C, (uint64_t)p.v_stride[0] * 2};
-        const uint64_t so[4] = {(uint64_t)p.o_stride[1] * 2, 128, (uint64_t)p.o_stride[1] * 2 * C, (uint64_t)p.o_stride[0] * 2};
-        int rc = make_tmap(&mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.v, dims, sv, boxv, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc == 0) rc = make_tmap(&mo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.o, dims, so, boxo, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc != 0) return (int)cudaErrorInvalidValue;
-    }
+    const int me = make_maps(p, C, F, &mq, &mk, &mv, &mo);
+    if (me != 0) return me;
     // time segments (see the header comment): explicit count in flags bits 8-11, else the simulated optimum; a launch
     // under stream capture stays uncut (no workspace allocation inside a graph)
     const int chains = p.B * p.H, cpf = (C + 63) / 64, nc = F * cpf;
@@ -993,15 +1137,69 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
         } else {
             xstate = reinterpret_cast<float*>(ws);
             xsync = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + state_bytes);
-            const cudaError_t me = cudaMemsetAsync(xsync, 0, sync_bytes, stream);
-            if (me != cudaSuccess) { cudaFreeAsync(ws, stream); return (int)me; }
+            const cudaError_t me2 = cudaMemsetAsync(xsync, 0, sync_bytes, stream);
+            if (me2 != cudaSuccess) { cudaFreeAsync(ws, stream); return (int)me2; }
         }
     }
-    gdr_chunk_kernel<<<chains * nseg, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, C, F, FastDiv::make((unsigned)cpf),
-                                                                      nseg, seg_chunks, xstate, xsync);
+    gdr_chunk_kernel<false><<<chains * nseg, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, C, F, FastDiv::make((unsigned)cpf),
+                                                                             nseg, seg_chunks, xstate, xsync, nullptr);
     count_launch();
     const cudaError_t le = cudaGetLastError();
     if (ws != nullptr) cudaFreeAsync(ws, stream);
+    return (int)le;
+}
+
+int chunked_varlen_seg_chunks(const GdkvmGdrParams& p, int nseq, int sms) {
+    // the lengths live on the device: plan for the average sequence (longer ones simply get more units of this size)
+    const int avg = std::max(1, (int)(((int64_t)p.T / std::max(1, nseq) + 63) / 64));
+    int nseg = (int)((p.flags >> 8) & 0xfu);
+    if (nseg == 0) nseg = pick_segments(nseq * p.H, avg, sms > 0 ? sms : 148);
+    nseg = std::max(1, std::min(nseg, avg));
+    return (avg + nseg - 1) / nseg;
+}
+
+// Packed variable-length sequences: q,k,v,o [1, T, H, *], sequence n = rows cu[n] .. cu[n+1]-1 (offsets on the device,
+// int32 or int64), states [nseq, H, K, V].
+int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream) {
+    const int ae = ensure_smem_attr();
+    if (ae != 0) return ae;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+        (void)cudaGetLastError();
+        return (int)cudaErrorStreamCaptureUnsupported;              // needs a per-launch workspace
+    }
+    CUtensorMap mq, mk, mv, mo;
+    const int me = make_maps(p, p.T, 1, &mq, &mk, &mv, &mo);
+    if (me != 0) return me;
+    const int H = p.H, V = p.V, chains = nseq * H;
+    const int seg_chunks = chunked_varlen_seg_chunks(p, nseq, device_sm_count());
+    // sum over sequences of round(chunks_n / seg_chunks)  <=  nseq + (sum of chunks) / seg_chunks,  sum of chunks <= T / 64 + nseq
+    const int64_t max_entries64 = (int64_t)nseq + ((int64_t)p.T / 64 + nseq) / seg_chunks + 1;
+    if (max_entries64 * H > 0x3fffffff) return (int)cudaErrorInvalidValue;
+    const int max_entries = (int)max_entries64;
+    const size_t state_bytes = (size_t)chains * 64 * V * sizeof(float);
+    const size_t sync_bytes = (((size_t)chains * 2 + 1) * sizeof(int) + 15) & ~(size_t)15;
+    const size_t tab_bytes = (size_t)kUnitInts * (1 + (size_t)max_entries) * sizeof(int);
+    void* ws = nullptr;
+    cudaError_t e = cudaMallocAsync(&ws, state_bytes + sync_bytes + tab_bytes, stream);
+    if (e != cudaSuccess) return (int)e;
+    float* xstate = reinterpret_cast<float*>(ws);
+    int* xsync = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + state_bytes);
+    int* utab = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + state_bytes + sync_bytes);
+    e = cudaMemsetAsync(xsync, 0, sync_bytes, stream);
+    if (e != cudaSuccess) { cudaFreeAsync(ws, stream); return (int)e; }
+    if (cu_bytes == 8)
+        gdr_units_kernel<long long><<<1, 256, 0, stream>>>(reinterpret_cast<const long long*>(cu), nseq, seg_chunks, max_entries, utab, H,
+                                                           64 * V, p.initial_state, p.final_state);
+    else
+        gdr_units_kernel<int><<<1, 256, 0, stream>>>(reinterpret_cast<const int*>(cu), nseq, seg_chunks, max_entries, utab, H, 64 * V,
+                                                     p.initial_state, p.final_state);
+    count_launch();
+    gdr_chunk_kernel<true><<<max_entries * H, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, p.T, 1, FastDiv::make(1u), 0, 0, xstate,
+                                                                              xsync, utab);
+    count_launch();
+    const cudaError_t le = cudaGetLastError();
+    cudaFreeAsync(ws, stream);
     return (int)le;
 }
 

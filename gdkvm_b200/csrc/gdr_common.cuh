@@ -12,6 +12,9 @@ namespace gdkvm {
 // Launchers (defined in gdr_recurrent.cu / gdr_chunked_sm100.cu). Return a cudaError_t as int.
 int launch_recurrent(const GdkvmGdrParams& p, cudaStream_t stream);
 int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream);
+// Packed variable-length sequences (q,k,v,o [1, T, H, *]; device-resident offsets cu[0..nseq], cu_bytes = 4 | 8; states [nseq, H, K, V])
+int launch_recurrent_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream);
+int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream);
 int launch_l2norm(const void* x, void* y, int64_t rows, int D, int64_t xs, int64_t ys, int dtype, float eps, cudaStream_t stream);
 // Host-side eligibility test of the chunked tcgen05 kernel (no GPU needed).
 bool chunked_supports(const GdkvmGdrParams& p);

@@ -40,7 +40,7 @@ __device__ __forceinline__ void load_vec(const TIO* __restrict__ ptr, float (&ou
 }
 
 template <int K, typename TIO>
-__global__ void __launch_bounds__(kThreads, (K <= 64 ? 3 : 1)) gdr_recurrent_kernel(const GdkvmGdrParams p) {
+__global__ void __launch_bounds__(kThreads, (K <= 64 ? 3 : 1)) gdr_recurrent_kernel(const GdkvmGdrParams p, const void* __restrict__ cu, const int cu_bytes) {
     constexpr int TB = K >= 128 ? 8 : 16;   // tokens per staged tile (keeps static smem < 48 KB)
     constexpr int EPT = TB * K / kThreads;  // q/k elements each thread stages per tile
     static_assert(EPT >= 4 && K % EPT == 0, "unsupported K");
@@ -53,17 +53,25 @@ __global__ void __launch_bounds__(kThreads, (K <= 64 ? 3 : 1)) gdr_recurrent_ker
 
     const int tid = threadIdx.x;
     const int chain = blockIdx.x;
-    const int b = chain / p.H, h = chain % p.H;
+    int b = chain / p.H;
+    const int h = chain % p.H;
     const int x = blockIdx.y * kThreads + tid;
     const bool col_ok = x < p.V;
-    const int T = p.T, V = p.V;
+    int T = p.T;
+    const int V = p.V;
+    int64_t tok0 = 0;
+    if (cu != nullptr) {   // packed variable-length sequences: chain = (sequence, head), rows cu[seq] .. cu[seq+1]-1 of clip 0
+        const int64_t lo = cu_bytes == 8 ? reinterpret_cast<const long long*>(cu)[b] : reinterpret_cast<const int*>(cu)[b];
+        const int64_t hi = cu_bytes == 8 ? reinterpret_cast<const long long*>(cu)[b + 1] : reinterpret_cast<const int*>(cu)[b + 1];
+        tok0 = lo; T = (int)(hi - lo); b = 0;
+    }
 
-    const TIO* q_base = reinterpret_cast<const TIO*>(p.q) + (int64_t)b * p.q_stride[0] + (int64_t)h * p.q_stride[2];
-    const TIO* k_base = reinterpret_cast<const TIO*>(p.k) + (int64_t)b * p.k_stride[0] + (int64_t)h * p.k_stride[2];
-    const TIO* v_base = reinterpret_cast<const TIO*>(p.v) + (int64_t)b * p.v_stride[0] + (int64_t)h * p.v_stride[2];
-    TIO* o_base = reinterpret_cast<TIO*>(p.o) + (int64_t)b * p.o_stride[0] + (int64_t)h * p.o_stride[2];
-    const int64_t g_off = (int64_t)b * p.g_stride[0] + (int64_t)h * p.g_stride[2];
-    const int64_t bt_off = (int64_t)b * p.beta_stride[0] + (int64_t)h * p.beta_stride[2];
+    const TIO* q_base = reinterpret_cast<const TIO*>(p.q) + (int64_t)b * p.q_stride[0] + (int64_t)h * p.q_stride[2] + tok0 * p.q_stride[1];
+    const TIO* k_base = reinterpret_cast<const TIO*>(p.k) + (int64_t)b * p.k_stride[0] + (int64_t)h * p.k_stride[2] + tok0 * p.k_stride[1];
+    const TIO* v_base = reinterpret_cast<const TIO*>(p.v) + (int64_t)b * p.v_stride[0] + (int64_t)h * p.v_stride[2] + tok0 * p.v_stride[1];
+    TIO* o_base = reinterpret_cast<TIO*>(p.o) + (int64_t)b * p.o_stride[0] + (int64_t)h * p.o_stride[2] + tok0 * p.o_stride[1];
+    const int64_t g_off = (int64_t)b * p.g_stride[0] + (int64_t)h * p.g_stride[2] + tok0 * p.g_stride[1];
+    const int64_t bt_off = (int64_t)b * p.beta_stride[0] + (int64_t)h * p.beta_stride[2] + tok0 * p.beta_stride[1];
 
     // state column in registers
     float S[K];
@@ -166,21 +174,23 @@ __global__ void __launch_bounds__(kThreads, (K <= 64 ? 3 : 1)) gdr_recurrent_ker
 }
 
 template <int K>
-int launch_k(const GdkvmGdrParams& p, cudaStream_t stream) {
-    dim3 grid(p.B * p.H, (p.V + kThreads - 1) / kThreads);
-    if (p.io_dtype == GDKVM_BF16) gdr_recurrent_kernel<K, __nv_bfloat16><<<grid, kThreads, 0, stream>>>(p);
-    else gdr_recurrent_kernel<K, float><<<grid, kThreads, 0, stream>>>(p);
+int launch_k(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream) {
+    dim3 grid((cu != nullptr ? nseq : p.B) * p.H, (p.V + kThreads - 1) / kThreads);
+    if (p.io_dtype == GDKVM_BF16) gdr_recurrent_kernel<K, __nv_bfloat16><<<grid, kThreads, 0, stream>>>(p, cu, cu_bytes);
+    else gdr_recurrent_kernel<K, float><<<grid, kThreads, 0, stream>>>(p, cu, cu_bytes);
     count_launch();
     return (int)cudaGetLastError();
 }
 
 }  // namespace
 
-int launch_recurrent(const GdkvmGdrParams& p, cudaStream_t stream) {
+int launch_recurrent(const GdkvmGdrParams& p, cudaStream_t stream) { return launch_recurrent_varlen(p, nullptr, 0, 0, stream); }
+
+int launch_recurrent_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream) {
     switch (p.K) {
-        case 32: return launch_k<32>(p, stream);
-        case 64: return launch_k<64>(p, stream);
-        case 128: return launch_k<128>(p, stream);
+        case 32: return launch_k<32>(p, cu, cu_bytes, nseq, stream);
+        case 64: return launch_k<64>(p, cu, cu_bytes, nseq, stream);
+        case 128: return launch_k<128>(p, cu, cu_bytes, nseq, stream);
         default: return (int)cudaErrorInvalidValue;
     }
 }

@@ -254,6 +254,31 @@ __device__ __forceinline__ void umma_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint
         ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
 }
+// Four K-slices of one 64-deep contraction behind ONE election: the operand moves into uniform registers of all
+// four MMAs are issued back to back instead of one dependent elect / move / issue sequence per MMA (~100 cycles each).
+__device__ __forceinline__ void umma4_ss_w(uint32_t d_tmem, uint64_t a0, uint64_t a1, uint64_t a2, uint64_t a3, uint64_t b0, uint64_t b1,
+                                           uint64_t b2, uint64_t b3, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %10, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %5, %9, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %2, %6, %9, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %7, %9, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %4, %8, %9, 1;\n\t}\n"
+        ::"r"(d_tmem), "l"(a0), "l"(a1), "l"(a2), "l"(a3), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma4_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t b0, uint64_t b1, uint64_t b2, uint64_t b3,
+                                           uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 a1, a2, a3;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %7, 0;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %6, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], %3, %6, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], %4, %6, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], %5, %6, 1;\n\t}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"

@@ -4,7 +4,9 @@
 readout and final state in pinned HOST tensors.  Clips are independent, so the batch is cut into
 groups of clips and the three legs -- host->device copy, GDR/LKVA kernel, device->host copy -- run
 on three CUDA streams over a ring of device slots: the copy of group i+1 and the read-back of group
-i-1 overlap the kernel of group i.  This is the path bench.py times as ``e2e``.
+i-1 overlap the kernel of group i.  This is the path bench.py times as ``e2e``.  The call is PCIe-bound (the
+kernel is ~2 % of it): small groups (2 clips) keep the ramp-up copy and the final read-back short; measured on a
+B200 box, configs[1]: 51.9 ms per call against 51.5 ms for the bytes at the duplex copy rate (scripts/e2e_sweep.py).
 """
 from __future__ import annotations
 
@@ -32,7 +34,7 @@ class HostPipeline:
     """Reusable host->B200->host pipeline for one problem geometry."""
 
     def __init__(self, B, T, H, K, V, io_dtype=torch.bfloat16, gate_dtype=torch.float32,
-                 clips_per_group: int = 8, slots: int = 3, device=None, with_initial_state: bool = True):
+                 clips_per_group: int = 2, slots: int = 3, device=None, with_initial_state: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("HostPipeline needs a CUDA device (B200); gdkvm_b200 has no CPU path")
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -98,7 +100,7 @@ class HostPipeline:
 
 
 def gdr_lkva_host(q, k, v, g, beta, scale=None, initial_state=None, frame_tokens: int = 0,
-                  clips_per_group: int = 8, flags: int = 0):
+                  clips_per_group: int = 2, flags: int = 0):
     """One-shot convenience wrapper around ``HostPipeline`` for pinned (or pageable) host tensors."""
     B, T, H, K = k.shape
     V = v.shape[-1]

@@ -22,7 +22,8 @@ import torch
 
 from . import _cabi
 
-__all__ = ["gdr_lkva", "gdr_lkva_out", "chunk_gated_delta_rule", "l2norm", "plan", "launch_count"]
+__all__ = ["gdr_lkva", "gdr_lkva_out", "gdr_lkva_varlen", "chunk_gated_delta_rule", "l2norm", "plan", "plan_segments",
+           "launch_count"]
 
 _DT = {torch.float32: _cabi.GDKVM_F32, torch.bfloat16: _cabi.GDKVM_BF16}
 
@@ -133,6 +134,53 @@ def _gdr_lkva_fake(q, k, v, g, beta, scale=None, initial_state=None, output_fina
     return o, sT
 
 
+torch.library.define(
+    "gdkvm::gdr_lkva_varlen",
+    "(Tensor q, Tensor k, Tensor v, Tensor g, Tensor beta, Tensor cu_seqlens, float? scale=None, "
+    "Tensor? initial_state=None, bool output_final_state=True, int flags=0) -> (Tensor, Tensor)",
+)
+
+
+@torch.library.impl("gdkvm::gdr_lkva_varlen", "CUDA")
+def _gdr_lkva_varlen_cuda(q, k, v, g, beta, cu_seqlens, scale=None, initial_state=None, output_final_state=True, flags=0):
+    _check(q, k, v, g, beta, None)
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    if B != 1:
+        raise ValueError("packed variable-length clips: q,k,v must be [1, total_tokens, H, *]")
+    if cu_seqlens.dim() != 1 or cu_seqlens.numel() < 2 or cu_seqlens.dtype not in (torch.int32, torch.int64):
+        raise ValueError("cu_seqlens must be a 1-D int32/int64 tensor of n_seqs + 1 offsets")
+    if not cu_seqlens.is_cuda:
+        raise ValueError("cu_seqlens must live on the device (it is never read on the host)")
+    N = cu_seqlens.numel() - 1
+    cu = cu_seqlens.contiguous()
+    if initial_state is not None:
+        if initial_state.shape != (N, H, K, V) or initial_state.dtype != torch.float32:
+            raise ValueError("initial_state must be fp32 [n_seqs,H,K,V]")
+        initial_state = initial_state.contiguous()
+    o = torch.empty((1, T, H, V), dtype=q.dtype, device=q.device)
+    sT = torch.empty((N, H, K, V) if output_final_state else (0,), dtype=torch.float32, device=q.device)
+    if scale is None:
+        scale = 1.0 / math.sqrt(K)
+    p = _make_params(q, k, v, g, beta, o, initial_state, sT if output_final_state else None, scale, 0, flags)
+    lib = _cabi.load()
+    with torch.cuda.device(q.device):
+        rc = lib.gdkvm_gdr_fwd_varlen(ctypes.byref(p), ctypes.c_void_p(cu.data_ptr()), cu.element_size(), N,
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        extra = f" (cudaError {lib.gdkvm_last_cuda_error()})" if rc == -7 else ""
+        raise RuntimeError(f"gdkvm_gdr_fwd_varlen: {_cabi.strerror(rc)}{extra}")
+    return o, sT
+
+
+@torch.library.register_fake("gdkvm::gdr_lkva_varlen")
+def _gdr_lkva_varlen_fake(q, k, v, g, beta, cu_seqlens, scale=None, initial_state=None, output_final_state=True, flags=0):
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    N = cu_seqlens.shape[0] - 1
+    return q.new_empty((1, T, H, V)), q.new_empty((N, H, K, V) if output_final_state else (0,), dtype=torch.float32)
+
+
 torch.library.define("gdkvm::l2norm", "(Tensor x, float eps=1e-6) -> Tensor")
 
 
@@ -180,15 +228,32 @@ def gdr_lkva(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, g: torch.Tensor,
     return o, (sT if output_final_state else None)
 
 
+def gdr_lkva_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, g: torch.Tensor, beta: torch.Tensor,
+                    cu_seqlens: torch.Tensor, scale: Optional[float] = None, initial_state: Optional[torch.Tensor] = None,
+                    output_final_state: bool = True, flags: int = 0) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """The memory op over PACKED clips of different lengths (fla's ``cu_seqlens``, fla/ops/gated_delta_rule/chunk.py:375).
+
+    q,k [1,T,H,K]; v [1,T,H,V]; g,beta [1,T,H]; ``cu_seqlens`` int32/int64 [N+1] ON THE DEVICE (clip n = rows
+    cu_seqlens[n] .. cu_seqlens[n+1]-1); initial_state fp32 [N,H,K,V].  Returns ``(o [1,T,H,V], final_state [N,H,K,V] or
+    None)``.  Nothing is read back to the host: the work-unit table is built on the device.
+    """
+    o, sT = torch.ops.gdkvm.gdr_lkva_varlen(q, k, v, g, beta, cu_seqlens, scale, initial_state, output_final_state, flags)
+    return o, (sT if output_final_state else None)
+
+
 def chunk_gated_delta_rule(q, k, v, g, beta, scale=None, initial_state=None, output_final_state=False,
                            **kwargs):
     """Name- and argument-compatible alias of fla's entry point (fla/ops/gated_delta_rule/chunk.py:365)."""
     unsupported = {kk: vv for kk, vv in kwargs.items()
-                   if kk not in ("frame_tokens", "flags", "use_qk_l2norm_in_kernel") and vv is not None and vv is not False}
+                   if kk not in ("frame_tokens", "flags", "use_qk_l2norm_in_kernel", "cu_seqlens") and vv is not None
+                   and vv is not False}
     if unsupported:
         raise NotImplementedError(f"gdkvm_b200.chunk_gated_delta_rule: unsupported arguments {sorted(unsupported)}")
     if kwargs.get("use_qk_l2norm_in_kernel"):      # one streaming CUDA pass each (not yet fused into the chunk kernel)
         q, k = l2norm(q), l2norm(k)
+    if kwargs.get("cu_seqlens") is not None:
+        return gdr_lkva_varlen(q, k, v, g, beta, kwargs["cu_seqlens"], scale, initial_state, output_final_state,
+                               kwargs.get("flags", 0))
     return gdr_lkva(q, k, v, g, beta, scale, initial_state, output_final_state,
                     kwargs.get("frame_tokens", 0), kwargs.get("flags", 0))
 

@@ -113,6 +113,21 @@ int gdkvm_last_cuda_error(void);
 int gdkvm_gdr_fwd(const GdkvmGdrParams* params, void* cuda_stream);
 
 /*
+ * The same op over PACKED variable-length clips (videos of different lengths in one batch):
+ *   replaces: the `cu_seqlens` argument of fla's chunk_gated_delta_rule (fla/ops/gated_delta_rule/chunk.py:375);
+ *   SURVEY.md section 8f rank 4.
+ * params->B must be 1 and params->T the total number of tokens: q,k [1,T,H,K], v,o [1,T,H,V], g,beta [1,T,H].  Clip n
+ * is rows cu_seqlens[n] .. cu_seqlens[n+1]-1 (n = 0..n_seqs-1; cu_seqlens[0] = 0, cu_seqlens[n_seqs] = T,
+ * non-decreasing), an array of n_seqs+1 offsets in DEVICE memory of cu_seqlens_bytes (4 or 8) bytes each -- the
+ * library never reads it on the host, so the call stays asynchronous.  initial_state / final_state are
+ * [n_seqs, H, K, V]; a clip without tokens passes its initial state through.  frame_tokens is ignored (flat 64-token
+ * tiling; token-causal semantics make that exactly equivalent).  Uses a stream-ordered per-launch workspace, so it
+ * cannot be captured into a CUDA graph (GDKVM_ERR_CUDA, cudaErrorStreamCaptureUnsupported).
+ */
+int gdkvm_gdr_fwd_varlen(const GdkvmGdrParams* params, const void* cu_seqlens, int32_t cu_seqlens_bytes, int32_t n_seqs,
+                         void* cuda_stream);
+
+/*
  * Which kernel gdkvm_gdr_fwd would pick for `params` without launching anything:
  * 0 = recurrent fp32 CUDA-core kernel, 1 = tcgen05 chunked kernel, negative = GdkvmStatus.
  * Needs no GPU.

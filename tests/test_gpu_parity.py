@@ -306,6 +306,91 @@ def test_time_segments_with_slow_path_chunks(op):
         assert torch.equal(o, o1) and torch.equal(sT, s1), n
 
 
+def _packed(lens, H, V, seed, dtype=torch.bfloat16, K=64):
+    """Clips of the given lengths packed back to back: ([1,T,H,*] tensors, cu_seqlens, per-clip views, S0 [N,H,K,V])."""
+    T = sum(lens)
+    q, k, v, g, beta, _ = make_inputs(1, max(T, 1), H, K, V, seed=seed, dtype=dtype)
+    q, k, v, g, beta = (t[:, :T] for t in (q, k, v, g, beta))
+    gen = torch.Generator().manual_seed(seed + 1)
+    S0 = 0.1 * torch.randn(len(lens), H, K, V, generator=gen)
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int64)
+    return q, k, v, g, beta, S0, cu
+
+
+def _varlen_ref(q, k, v, g, beta, S0, cu):
+    o = torch.zeros(1, q.shape[1], q.shape[2], v.shape[-1])
+    sT = torch.zeros_like(S0)
+    for n in range(len(cu) - 1):
+        a, b = int(cu[n]), int(cu[n + 1])
+        if b == a:
+            sT[n] = S0[n]
+            continue
+        o_n, s_n = gdr_recurrent_ref(q[:, a:b], k[:, a:b], v[:, a:b], g[:, a:b], beta[:, a:b], None, S0[n:n + 1])
+        o[:, a:b] = o_n
+        sT[n] = s_n[0]
+    return o, sT
+
+
+@pytest.mark.parametrize("case", [
+    # lens, H, V, dtype, flags
+    ([200, 64, 1, 333, 128, 17], 2, 256, torch.bfloat16, CHUNKED),          # ragged tails, exact chunks, single token
+    ([700, 0, 65, 0, 1290], 3, 128, torch.bfloat16, CHUNKED | SEG(3)),       # empty clips, forced time segments, V = 128
+    ([16 * 64, 64, 10 * 64], 2, 256, torch.bfloat16, CHUNKED | SEG(3)),      # 3-chunk target segments: 16 chunks -> 4+4+4+4
+    ([5, 9, 130], 2, 40, torch.float32, 0),                                  # fp32 I/O -> recurrent kernel
+    ([100, 37, 260], 2, 256, torch.bfloat16, RECURRENT),                     # recurrent kernel, bf16 I/O
+    ([64 * 30] * 5 + [64 * 7 + 3] * 6, 8, 256, torch.bfloat16, 0),           # many units, library-chosen segment length
+])
+@pytest.mark.parametrize("cu_dtype", [torch.int64, torch.int32], ids=["i64", "i32"])
+def test_varlen_packed_clips_vs_oracle(op, case, cu_dtype):
+    """Packed clips of different lengths (cu_seqlens on the device) against the per-clip CPU oracle: readout of every
+    clip, final state of every clip, nothing written outside a clip's rows."""
+    lens, H, V, dtype, flags = case
+    K = 64 if V != 40 else 32
+    q, k, v, g, beta, S0, cu = _packed(lens, H, V, 51, dtype, K)
+    o_ref, s_ref = _varlen_ref(q, k, v, g, beta, S0, cu)
+    qd, kd, vd, gd, bd, sd = _dev(q, k, v, g, beta, S0)
+    o, sT = op.gdr_lkva_varlen(qd, kd, vd, gd, bd, cu.to(cu_dtype).cuda(), None, sd, True, flags)
+    torch.cuda.synchronize()
+    tol = TOL[dtype]
+    assert max_rel_err(o.float().cpu(), o_ref) <= tol and max_rel_err(sT.cpu(), s_ref) <= tol
+    for n in range(len(lens)):                       # per clip (a short clip must not hide behind a long one's scale)
+        a, b = int(cu[n]), int(cu[n + 1])
+        if b > a:
+            assert max_rel_err(o[:, a:b].float().cpu(), o_ref[:, a:b]) <= tol, n
+        assert max_rel_err(sT[n].cpu(), s_ref[n]) <= tol, n
+
+
+def test_varlen_equals_batched_call_bit_for_bit(op):
+    """Equal-length clips: the packed call must reproduce the batched call exactly (same chunking, same arithmetic),
+    and chunk_gated_delta_rule(cu_seqlens=...) is the same entry point."""
+    B, T, H, V = 5, 6 * 64 + 21, 4, 256
+    q, k, v, g, beta, S0 = _dev(*make_inputs(B, T, H, 64, V, seed=52, dtype=torch.bfloat16))
+    o_b, s_b = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 0, CHUNKED)
+    pk = lambda t: t.reshape(1, B * T, *t.shape[2:])
+    cu = torch.arange(B + 1, device="cuda", dtype=torch.int32) * T
+    o_p, s_p = op.gdr_lkva_varlen(pk(q), pk(k), pk(v), pk(g), pk(beta), cu, None, S0, True, CHUNKED)
+    assert torch.equal(o_p.reshape(B, T, H, V), o_b) and torch.equal(s_p, s_b)
+    o_f, s_f = op.chunk_gated_delta_rule(pk(q), pk(k), pk(v), pk(g), pk(beta), initial_state=S0, output_final_state=True,
+                                         cu_seqlens=cu)
+    assert torch.equal(o_f, o_p) and torch.equal(s_f, s_p)
+    o_n, s_n = op.gdr_lkva_varlen(pk(q), pk(k), pk(v), pk(g), pk(beta), cu, None, None, False, CHUNKED | SEG(2))
+    o_b0, _ = op.gdr_lkva(q, k, v, g, beta, None, None, True, 0, CHUNKED)
+    assert s_n is None and torch.equal(o_n.reshape(B, T, H, V), o_b0)
+
+
+def test_varlen_rows_outside_every_clip_are_untouched(op):
+    """The last chunk of a clip is stored row by row: the readout rows of the NEXT clip must come from that clip only,
+    whatever order the work units finish in (run twice with a poisoned output buffer in between)."""
+    lens = [70, 3, 129, 64, 1]
+    q, k, v, g, beta, S0, cu = _packed(lens, 2, 256, 53)
+    qd, kd, vd, gd, bd, sd = _dev(q, k, v, g, beta, S0)
+    cud = cu.cuda()
+    o1, s1 = op.gdr_lkva_varlen(qd, kd, vd, gd, bd, cud, None, sd, True, CHUNKED)
+    for _ in range(3):
+        o2, s2 = op.gdr_lkva_varlen(qd, kd, vd, gd, bd, cud, None, sd, True, CHUNKED)
+        assert torch.equal(o1, o2) and torch.equal(s1, s2)
+
+
 @pytest.fixture(scope="module")
 def echonet_batch():
     """configs[1]: 64 clips x 128 frames x 49 tokens, 8 heads, K=64, V=256, bf16 -- built on the GPU."""
