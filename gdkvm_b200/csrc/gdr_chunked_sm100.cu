@@ -275,6 +275,22 @@ __device__ __forceinline__ void umma4_ts(uint32_t d, uint32_t a_tmem, uint64_t b
 #endif
 }
 
+// ... with the commit(s) that follow them behind the same election
+__device__ __forceinline__ void umma4_ts_commit(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t bstep, uint32_t idesc, bool acc0,
+                                                uint64_t* bar0, uint64_t* bar1 = nullptr) {
+#ifdef GDKVM_UMMA_SINGLE
+    umma4_ts(d, a_tmem, bdesc, bstep, idesc, acc0);
+    umma_commit_w(bar0);
+    if (bar1 != nullptr) umma_commit_w(bar1);
+#else
+    if (bar1 == nullptr)
+        umma4_ts_commit_w(d, a_tmem, bdesc, bdesc + (uint64_t)bstep, bdesc + (uint64_t)(2 * bstep), bdesc + (uint64_t)(3 * bstep), idesc, acc0, bar0);
+    else
+        umma4_ts_commit2_w(d, a_tmem, bdesc, bdesc + (uint64_t)bstep, bdesc + (uint64_t)(2 * bstep), bdesc + (uint64_t)(3 * bstep), idesc, acc0,
+                           bar0, bar1);
+#endif
+}
+
 // n / d for 0 <= n < 2^31 and a run-time d >= 1 without the ~40-instruction integer division sequence (the kernel is
 // instruction-issue bound and maps chunk -> (frame, chunk in frame) several times per chunk).  Host-side constants.
 struct FastDiv {
@@ -840,8 +856,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 PT(33, lane == 0 && hh == 0, n);   // issuer S: wait W^T operand
                 mbar_wait_inl(&bars[kSbReady + hh], par1);
                 tc_fence_after_sync();
-                umma4_ts(tVn, tSb, dWt, 128, kIdMnBneg, true);                                      // Vn^T -= Sb W^T
-                umma_commit_w(&bars[kVnFull + hh]);
+                umma4_ts_commit(tVn, tSb, dWt, 128, kIdMnBneg, true, &bars[kVnFull + hh]);          // Vn^T -= Sb W^T
                 PT(34, lane == 0 && hh == 0, n);   // issuer S: wait Sb, issue Vn correction
                 if (n >= 1) mbar_wait_inl(&bars[kOFree + hh], par1 ^ 1u);
                 tc_fence_after_sync();
@@ -849,11 +864,8 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 PT(35, lane == 0 && hh == 0, n);   // issuer S: wait O free, issue inter-chunk readout
                 mbar_wait_inl(&bars[kVnbReady + hh], par1);
                 tc_fence_after_sync();
-                umma4_ts(tS, tVn + vn_off, dKp, 128, kIdMnB, true);                                  // S^T += Vnb K'
-                umma_commit_w(&bars[kSReady + hh]);
-                umma4_ts(tO, tVn, dPp, 2, kIdKK, true);                                              // O^T += Vnb P^T
-                umma_commit_w(&bars[kOFull + hh]);
-                umma_commit_w(&bars[kKsideEmpty + st]);                                              // one of NH arrivals
+                umma4_ts_commit(tS, tVn + vn_off, dKp, 128, kIdMnB, true, &bars[kSReady + hh]);     // S^T += Vnb K'
+                umma4_ts_commit(tO, tVn, dPp, 2, kIdKK, true, &bars[kOFull + hh], &bars[kKsideEmpty + st]);   // O^T += Vnb P^T; one of NH arrivals
                 if (n + 2 < NC) {   // U of chunk n completed before Vnb was published: its V half-tile slot takes chunk n + 2
                     if (elect_one()) {
                         int c0, f;

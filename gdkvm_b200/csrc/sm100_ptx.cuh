@@ -279,6 +279,35 @@ __device__ __forceinline__ void umma4_ts_w(uint32_t d_tmem, uint32_t a_tmem, uin
         ::"r"(d_tmem), "r"(a_tmem), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"((uint32_t)accumulate)
         : "memory");
 }
+// ... followed by commits on one or two mbarriers, still behind the same election
+__device__ __forceinline__ void umma4_ts_commit_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t b0, uint64_t b1, uint64_t b2, uint64_t b3,
+                                                  uint32_t idesc, bool accumulate, uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 a1, a2, a3;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %7, 0;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %6, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], %3, %6, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], %4, %6, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], %5, %6, 1;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"((uint32_t)accumulate), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void umma4_ts_commit2_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t b0, uint64_t b1, uint64_t b2, uint64_t b3,
+                                                   uint32_t idesc, bool accumulate, uint64_t* bar0, uint64_t* bar1) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b32 a1, a2, a3;\n\telect.sync _|q, 0xffffffff;\n\tsetp.ne.b32 p, %7, 0;\n\t"
+        "add.u32 a1, %1, 8;\n\tadd.u32 a2, %1, 16;\n\tadd.u32 a3, %1, 24;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %6, p;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], %3, %6, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], %4, %6, 1;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], %5, %6, 1;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t}\n"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b0), "l"(b1), "l"(b2), "l"(b3), "r"(idesc), "r"((uint32_t)accumulate), "r"(smem_u32(bar0)),
+          "r"(smem_u32(bar1))
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
     asm volatile(
         "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"

@@ -360,6 +360,25 @@ def test_varlen_packed_clips_vs_oracle(op, case, cu_dtype):
         assert max_rel_err(sT[n].cpu(), s_ref[n]) <= tol, n
 
 
+def test_varlen_many_short_clips(op, c_oracle):
+    """700 clips of 0..130 tokens (several rounds of the 256-thread table builder, most clips a single ragged chunk)."""
+    rng = np.random.default_rng(54)
+    lens = [int(x) for x in rng.integers(0, 131, size=700)]
+    q, k, v, g, beta, S0, cu = _packed(lens, 2, 256, 55)
+    qd, kd, vd, gd, bd, sd = _dev(q, k, v, g, beta, S0)
+    o, sT = op.gdr_lkva_varlen(qd, kd, vd, gd, bd, cu.cuda(), None, sd, True, 0)
+    o_r, s_r = op.gdr_lkva_varlen(qd, kd, vd, gd, bd, cu.cuda(), None, sd, True, RECURRENT)     # fp32-exact CUDA-core path
+    torch.cuda.synchronize()
+    assert max_rel_err(o, o_r) <= 2e-2 and max_rel_err(sT, s_r) <= 2e-2
+    for n in (0, 1, 2, 350, 698, 699):                                    # spot-check clips against the CPU oracle
+        a, b = int(cu[n]), int(cu[n + 1])
+        if b == a:
+            assert torch.equal(sT[n].cpu(), S0[n])
+            continue
+        o_ref, s_ref = c_oracle.gdr_recurrent_c(q[:, a:b], k[:, a:b], v[:, a:b], g[:, a:b], beta[:, a:b], None, S0[n:n + 1])
+        assert max_rel_err(o[:, a:b].float().cpu(), o_ref) <= 2e-2 and max_rel_err(sT[n:n + 1].cpu(), s_ref) <= 2e-2, n
+
+
 def test_varlen_equals_batched_call_bit_for_bit(op):
     """Equal-length clips: the packed call must reproduce the batched call exactly (same chunking, same arithmetic),
     and chunk_gated_delta_rule(cu_seqlens=...) is the same entry point."""
