@@ -11,7 +11,7 @@
 //     S^T  = gamma S^T + Vnb K'          (fp32 accumulate in place)
 // Every contraction is a 128 x 64 x 64 tcgen05.mma (bf16 in, fp32 TMEM accumulate).
 //
-// Roles (19 warps):
+// Roles (20 warps):
 //   warps 0-7   K-side group: everything that does not depend on the state, one chunk AHEAD of the
 //               state side: [K;Q]K^T accumulators -> masked/gated A (fp32) and P (bf16); the
 //               triangular inverse (I + A)^-1 in fp32-grade arithmetic (16x16 forward substitution on
@@ -21,6 +21,7 @@
 //               readout O -> bf16 -> staging -> TMA store; initial / final state.
 //   warp 16     issuer K: TMA loads (q, k, v tiles, one chunk of prefetch) and the K-side MMAs.
 //   warps 17-18  issuers S: the five state-side MMA groups of one value half each.
+//   warp 19     idle: completes the issuer warpgroup, which gives most of its registers to the state warpgroups.
 // The roles meet only through mbarriers (tcgen05.commit / arrive), so the K-side work of chunk n+1,
 // the state-side work of chunk n and the TMA traffic of chunk n+2 overlap.
 //
@@ -70,7 +71,12 @@ namespace {
 using namespace sm100;
 
 constexpr int kKThreads = 256;                 // K-side group
-constexpr int kThreads = 19 * 32;              // whole CTA (at most 5 warps per scheduler: 96 registers per thread)
+// 19 working warps + one idle warp that completes the issuer warpgroup (setmaxnreg works on whole warpgroups).  The CTA
+// starts with 96 registers per thread (5 warps per scheduler: 480 of its 512 registers per lane); the issuer warpgroup then
+// shrinks to 40 and the two state warpgroups grow to kStateRegs: per scheduler 2 x 96 + 2 x 120 + 40 = 472.  With 96
+// registers the Vnb pass (64 fp32 accumulator values per thread in flight) saved and restored 14 registers around its
+// TMEM loads, on the recurrence: 0 spill bytes now, -2.1 % (scripts/ab.sh).
+constexpr int kThreads = 20 * 32;
 
 // ---- shared memory map (bytes from a 1024-aligned base) ----
 // Two TMA rings with different lifetimes: the K|Q tiles of a chunk live from the K side of the chunk (one
@@ -252,6 +258,17 @@ __device__ __forceinline__ void w_unit_mma(uint32_t aK, uint32_t aT, uint8_t* wt
         const int i0 = ng * 32 + nt * 8 + 2 * t;
         *reinterpret_cast<uint32_t*>(wt + sw128_offset(mt * 16 + g, i0 >> 3) + (i0 & 7) * 2) = pack_bf16(acc[nt][0], acc[nt][1]);
         *reinterpret_cast<uint32_t*>(wt + sw128_offset(mt * 16 + g + 8, i0 >> 3) + (i0 & 7) * 2) = pack_bf16(acc[nt][2], acc[nt][3]);
+    }
+}
+
+// Rows 0 .. valid-1 of one value half of the readout staging tile ([2 value blocks][64 tokens][64] bf16, 128B swizzle)
+// -> global memory with 16-byte stores, by the 128 threads of a state warpgroup.  Out of line on purpose: it runs once
+// per clip and must not add to the register pressure of the readout it is called from.
+__device__ __noinline__ void store_valid_rows(const uint8_t* stage, __nv_bfloat16* og, int64_t row_stride, int valid, int stid) {
+    for (int idx = stid; idx < valid * 16; idx += 128) {
+        const int row = idx >> 4, blk = (idx >> 3) & 1, ck = idx & 7;
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + blk * 8192 + sw128_offset(row, ck));
+        *reinterpret_cast<uint4*>(og + (int64_t)row * row_stride + blk * 64 + ck * 8) = val;
     }
 }
 
@@ -588,6 +605,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
         // =========================================================================================
         // state warpgroups (one per 128 value columns)
         // =========================================================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
         const int hh = (warp - 8) >> 2, wq = warp & 3, stid = tid - 256 - hh * 128;
         if (hh < NH) {
             const uint32_t lane_addr = tmem + ((uint32_t)(wq * 32) << 16);
@@ -658,14 +676,10 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 if (kVar && (int)s_info[6] - (m << 6) < 64) {
                     // last chunk of a packed sequence: the rows behind it belong to the next sequence, so the valid rows
                     // leave through ordinary 16-byte stores (staging tile: [value block][token][64], 128B swizzle)
-                    const int valid = (int)s_info[6] - (m << 6);
-                    __nv_bfloat16* og = reinterpret_cast<__nv_bfloat16*>(p.o) + ((int64_t)s_info[4] + (m << 6)) * p.o_stride[1] +
-                                        (int64_t)s_info[3] * p.o_stride[2] + hh * 128;
-                    for (int idx = stid; idx < valid * 16; idx += 128) {
-                        const int row = idx >> 4, blk = (idx >> 3) & 1, ck = idx & 7;
-                        const uint4 val = *reinterpret_cast<const uint4*>(smem + kOffOst + hh * 16384 + blk * 8192 + sw128_offset(row, ck));
-                        *reinterpret_cast<uint4*>(og + (int64_t)row * p.o_stride[1] + blk * 64 + ck * 8) = val;
-                    }
+                    store_valid_rows(smem + kOffOst + hh * 16384,
+                                     reinterpret_cast<__nv_bfloat16*>(p.o) + ((int64_t)s_info[4] + (m << 6)) * p.o_stride[1] +
+                                         (int64_t)s_info[3] * p.o_stride[2] + hh * 128,
+                                     p.o_stride[1], (int)s_info[6] - (m << 6), stid);
                 } else if (stid == 0) {
                     int c0, f;
                     chunk_coord(m, c0, f);
@@ -697,21 +711,33 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 {   // S_n = post_{n-1} * accumulator;  Sb = bf16(S_n) (operand copy);  accumulator <- pre_n * S_n
                     const float post = n >= 1 ? sPost[(n - 1) & 3] : 1.f, pre = sPre[n & 3];
                     const bool rescale = pre != 1.f || post != 1.f;
-#pragma unroll
-                    for (int half = 0; half < (ABL(5) ? 0 : 2); ++half) {
-                        uint32_t r[32], pk[16];
-                        tmem_ld32(lane_addr + kColS + hh * 64 + half * 32, r);
+                    if (!ABL(5)) {   // both 32-column halves in flight at once (one TMEM load latency instead of two)
+                        uint32_t ra[32], rb[32], pk[32];
+                        tmem_ld32(lane_addr + kColS + hh * 64, ra);
+                        tmem_ld32(lane_addr + kColS + hh * 64 + 32, rb);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * post);
+                        for (int j = 0; j < 32; ++j) {
+                            ra[j] = __float_as_uint(__uint_as_float(ra[j]) * post);
+                            rb[j] = __float_as_uint(__uint_as_float(rb[j]) * post);
+                        }
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-                        tmem_st16(lane_addr + kColSb + hh * 32 + half * 16, pk);
+                        for (int j = 0; j < 16; ++j) {
+                            pk[j] = pack_bf16(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1]));
+                            pk[16 + j] = pack_bf16(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1]));
+                        }
+                        tmem_st32(lane_addr + kColSb + hh * 32, pk);
                         if (pre != 1.f) {      // slow path only
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * pre);
+                            for (int j = 0; j < 32; ++j) {
+                                ra[j] = __float_as_uint(__uint_as_float(ra[j]) * pre);
+                                rb[j] = __float_as_uint(__uint_as_float(rb[j]) * pre);
+                            }
                         }
-                        if (rescale) tmem_st32(lane_addr + kColS + hh * 64 + half * 32, r);
+                        if (rescale) {
+                            tmem_st32(lane_addr + kColS + hh * 64, ra);
+                            tmem_st32(lane_addr + kColS + hh * 64 + 32, rb);
+                        }
                     }
                     tmem_wait_st();
                 }
@@ -725,10 +751,11 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 PT(20, tid == 256, n);   // wait: Vn
                 if (!ABL(6)) {   // Vnb = bf16(Vn^T) written over the first half of Vn (TMEM A-operand); both fp32 halves are
                     // in registers before the bf16 columns overwrite them
-                    uint32_t r0[32], r1[32], pk[32];
+                    uint32_t r0[32], r1[32];
                     tmem_ld32(lane_addr + kColVn + hh * 64, r0);
                     tmem_ld32(lane_addr + kColVn + hh * 64 + 32, r1);
                     tmem_wait_ld();
+                    uint32_t pk[32];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         pk[j] = pack_bf16(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
@@ -777,7 +804,9 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             if (stid == 0) tma_store_wait_all0();
             tc_fence_before_sync();
         }
-    } else if (warp == 16) {
+    } else {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");      // the whole issuer warpgroup (warps 16-19) at one instruction
+      if (warp == 16) {
         // =========================================================================================
         // issuer K: TMA loads (one chunk of prefetch) + the [K;Q]K^T MMA
         // =========================================================================================
@@ -823,7 +852,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 }
             }
         }
-    } else {
+      } else {
         // =========================================================================================
         // issuers S: the state-side MMAs, one warp per value half.  Issuing a tcgen05.mma costs ~100 cycles whenever
         // its descriptors have to be moved into uniform registers first (tests/probes/mma_timing.cu: 33 cycles only
@@ -880,6 +909,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             }
         }
         __syncwarp();
+      }
     }
 
     // ---- teardown ----
