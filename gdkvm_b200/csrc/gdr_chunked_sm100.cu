@@ -73,7 +73,8 @@ using namespace sm100;
 constexpr int kKThreads = 256;                 // K-side group
 // 19 working warps + one idle warp that completes the issuer warpgroup (setmaxnreg works on whole warpgroups).  The CTA
 // starts with 96 registers per thread (5 warps per scheduler: 480 of its 512 registers per lane); the issuer warpgroup then
-// shrinks to 40 and the two state warpgroups grow to kStateRegs: per scheduler 2 x 96 + 2 x 120 + 40 = 472.  With 96
+// shrinks to 40 and the two state warpgroups grow to 120.  An increase can only take what a decrease of the SAME CTA has
+// released (4 warps x 56 >= 8 warps x 24); asking for more (state 128, or K-side 112 as well) blocks forever.  With 96
 // registers the Vnb pass (64 fp32 accumulator values per thread in flight) saved and restored 14 registers around its
 // TMEM loads, on the recurrence: 0 spill bytes now, -2.1 % (scripts/ab.sh).
 constexpr int kThreads = 20 * 32;
