@@ -4,7 +4,8 @@
 // Block recursion over 16 x 16 blocks, operands and intermediates in registers (mma.sync m16n8k16 with
 // ldmatrix / stmatrix fragments; the accumulator of the first product is re-used as the A operand of the
 // second one), so a level needs no shared-memory round trip and no block-wide barrier:
-//   level 0  X_bb = (I + A_bb)^-1                       16-step forward substitution, fp32, 64 threads
+//   level 0    8 x 8 diagonal blocks: (I + A_bb)^-1       8-step forward substitution, fp32, 64 threads
+//   level 0.5  8 -> 16: X_ba = -(X_bb L_ba) X_aa          two mma per 16 x 16 block (zero-padded fragments), two blocks per warp
 //   level 1  X_ba = -(X_bb L_ba) X_aa                   (a, b) = (0,1), (2,3): one warp each
 //   level 2  [X_20 X_21; X_30 X_31] = -Xbr (Lbl Xtl)    four warps, one 16 x 16 output block each
 // On entry H holds A (strict lower triangle, zeros elsewhere, fp16); on exit H holds X = (I + A)^-1
@@ -44,6 +45,9 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], uint32_t addr) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
+__device__ __forceinline__ void ldsm_x1_trans(uint32_t& r, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x1.trans.shared.b16 {%0}, [%1];" : "=r"(r) : "r"(addr));
+}
 __device__ __forceinline__ void stsm_x4(uint32_t addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
                  : "memory");
@@ -78,28 +82,19 @@ __device__ __forceinline__ void store_neg_block(uint32_t h, int br, int bc, cons
 // Level 0 + level 1: warps 0 and 1 (64 threads).  Thread t of the pair: diagonal block t / 16, column t % 16.
 // hs = generic pointer to H, h = its shared-window address.
 __device__ __forceinline__ void solve_levels01(uint8_t* hs, uint32_t h, int warp, int lane) {
-    {
-        const int blk = 2 * warp + (lane >> 4), c = lane & 15;
-        float x[16];
+    {   // level 0: the eight 8 x 8 diagonal blocks, one column per thread: (I + L)^-1 e_c by forward substitution in fp32.
+        // Row i of block b8 is ONE 16-byte chunk (chunk b8 of row 8 b8 + i).
+        const int b8 = 4 * warp + (lane >> 3), c = lane & 7;
+        float x[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {       // row i of the block: 16 halves in chunks 2 blk, 2 blk + 1
-            const int row = 16 * blk + i;
+        for (int i = 0; i < 8; ++i) {
             float s = (i == c) ? 1.f : 0.f;
             if (i > 0) {
-                const uint4 lo = *reinterpret_cast<const uint4*>(hs + sw128_offset(row, 2 * blk));
-                const uint32_t w[4] = {lo.x, lo.y, lo.z, lo.w};
+                const uint4 rw = *reinterpret_cast<const uint4*>(hs + sw128_offset(8 * b8 + i, b8));
+                const uint32_t w[4] = {rw.x, rw.y, rw.z, rw.w};
 #pragma unroll
-                for (int j = 0; j < 8 && j < i; ++j) {
+                for (int j = 0; j < i; ++j) {
                     const float2 f = unpack_f16(w[j >> 1]);
-                    s = fmaf(-((j & 1) ? f.y : f.x), x[j], s);
-                }
-            }
-            if (i > 8) {
-                const uint4 hi = *reinterpret_cast<const uint4*>(hs + sw128_offset(row, 2 * blk + 1));
-                const uint32_t w[4] = {hi.x, hi.y, hi.z, hi.w};
-#pragma unroll
-                for (int j = 8; j < i; ++j) {
-                    const float2 f = unpack_f16(w[(j - 8) >> 1]);
                     s = fmaf(-((j & 1) ? f.y : f.x), x[j], s);
                 }
             }
@@ -107,8 +102,27 @@ __device__ __forceinline__ void solve_levels01(uint8_t* hs, uint32_t h, int warp
         }
         __syncwarp();                       // every row of the block has been read
 #pragma unroll
-        for (int i = 0; i < 16; ++i)        // column c of X_bb
-            *reinterpret_cast<__half*>(hs + sw128_offset(16 * blk + i, 2 * blk + (c >> 3)) + (c & 7) * 2) = __float2half_rn(x[i]);
+        for (int i = 0; i < 8; ++i)         // column c of the block's inverse
+            *reinterpret_cast<__half*>(hs + sw128_offset(8 * b8 + i, b8) + c * 2) = __float2half_rn(x[i]);
+        __syncwarp();
+    }
+    {   // level 0.5: 8 -> 16.  The 16 x 16 block B now reads M = [X_aa 0; L_ba X_bb]; one A fragment of M serves both
+        // products: M [0; L_ba] = [.; X_bb L_ba] and, with the lower accumulator rows re-used as A rows 8-15,
+        // [.; Q 0] [X_aa; 0] = [.; Q X_aa].  X_ba = -(X_bb L_ba) X_aa goes back over L_ba.
+        const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int B = 2 * warp + u;
+            uint32_t fm[4], bl, bx;
+            frag_a(fm, h, B, B, lane);
+            ldsm_x1_trans(bl, h + sw128_offset(16 * B + 8 + (lane & 7), 2 * B));
+            ldsm_x1_trans(bx, h + sw128_offset(16 * B + (lane & 7), 2 * B));
+            float q[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_f16(q, fm, 0u, bl);
+            const uint32_t fq[4] = {0u, pack_f16(q[2], q[3]), 0u, 0u};
+            mma_f16(r, fq, bx, 0u);
+            *reinterpret_cast<uint32_t*>(hs + sw128_offset(16 * B + 8 + g, 2 * B) + 4 * t) = pack_f16(-r[2], -r[3]);
+        }
         __syncwarp();
     }
     {   // X_ba = -(X_bb L_ba) X_aa
