@@ -92,8 +92,8 @@ constexpr uint32_t kOffTp = kOffWt + 16384;      // T'  [2]  (B of U / W, K-majo
 constexpr uint32_t kOffOst = kOffTp + 16384;     // readout staging, per value half [2][64 tok][64] bf16
 constexpr uint32_t kOffH = kOffOst + 32768;      // fp16 solve matrix (128B-swizzled rows, tri_solve.cuh)
 constexpr uint32_t kOffF = kOffH + 8192;
-//   floats: beta[2][64] Gam[2][64] E[4][64] Cj[2][64] Kd[4][64] Ofac[4][64] post[4] pre[4] fast[4]
-constexpr uint32_t kNumFloats = 18 * 64 + 12;
+//   floats: beta[2][64] Gam[2][64] E[4][64] Cj[2][64] Kd[4][64] Ofac[4][64] post[4] pre[4] fast[4] Eb[4][32] (bf16 pairs)
+constexpr uint32_t kNumFloats = 20 * 64 + 12;
 constexpr uint32_t kOffBar = kOffF + kNumFloats * 4;
 constexpr uint32_t kNumBars = 27;
 constexpr uint32_t kSmemBytes = kOffBar + kNumBars * 8 + 48 + 1024;   // + tmem slot + unit info + alignment slack
@@ -198,7 +198,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t add
 
 // Gate scan of one chunk (one warp; lane l holds g, beta of tokens 2l, 2l+1): Gamma = cumsum(g), decay
 // factors, fast/slow decision.
-__device__ __forceinline__ void gate_scan(const float (&gv)[2], const float (&bv)[2], float* sBt, float* sGam, float* sE,
+__device__ __forceinline__ void gate_scan(const float (&gv)[2], const float (&bv)[2], float* sBt, float* sGam, float* sE, uint32_t* sEb,
                                           float* sCj, float* sKd, float* sFast, float* ofac, float* post, float* pre,
                                           float scale, int lane) {
     const float g0 = gv[0], g1 = gv[1];
@@ -215,6 +215,7 @@ __device__ __forceinline__ void gate_scan(const float (&gv)[2], const float (&bv
     *reinterpret_cast<float2*>(sBt + 2 * lane) = make_float2(bv[0], bv[1]);
     *reinterpret_cast<float2*>(sGam + 2 * lane) = make_float2(G0, G1);
     *reinterpret_cast<float2*>(sE + 2 * lane) = make_float2(e0, e1);
+    sEb[lane] = pack_bf16(e0, e1);
     *reinterpret_cast<float2*>(sCj + 2 * lane) =                               // column factor of T'
         make_float2(bv[0] * (fast ? __expf(-G0) : 1.f), bv[1] * (fast ? __expf(-G1) : 1.f));
     *reinterpret_cast<float2*>(sKd + 2 * lane) = make_float2(__expf(Gl - G0), __expf(Gl - G1));   // slow path: K' factor
@@ -226,7 +227,7 @@ __device__ __forceinline__ void gate_scan(const float (&gv)[2], const float (&bv
 // bf16 mma.sync with ldmatrix from the 128B-swizzled K tile (transposed) and T' tile; e_j is applied to
 // the K fragments; the result is written as the bf16 MN-major operand rows of the Vn correction MMA
 // (row = key dim d, contiguous over tokens i).  T' is lower triangular: slices with j > i are skipped.
-__device__ __forceinline__ void w_unit_mma(uint32_t aK, uint32_t aT, uint8_t* wt, const float* eS, int mt, int ng, int lane) {
+__device__ __forceinline__ void w_unit_mma(uint32_t aK, uint32_t aT, uint8_t* wt, const uint32_t* eB, int mt, int ng, int lane) {
     const int g = lane >> 2, t = lane & 3;
     float acc[4][4];
 #pragma unroll
@@ -238,13 +239,14 @@ __device__ __forceinline__ void w_unit_mma(uint32_t aK, uint32_t aT, uint8_t* wt
         if (ks * 16 <= ng * 32 + 31) {
             uint32_t af[4], bf0[4], bf1[4];
             ldmatrix_x4_trans(af, aK + sw128_offset(ks * 16 + (lane & 7) + ((lane >> 4) & 1) * 8, mt * 2 + ((lane >> 3) & 1)));
-            {   // K~ = K e_j: fragment registers hold tokens j = 16 ks + 2t (+1) and + 8
-                const float2 e01 = *reinterpret_cast<const float2*>(eS + ks * 16 + 2 * t);
-                const float2 e89 = *reinterpret_cast<const float2*>(eS + ks * 16 + 2 * t + 8);
-                af[0] = pack_bf16(__uint_as_float(af[0] << 16) * e01.x, __uint_as_float(af[0] & 0xffff0000u) * e01.y);
-                af[1] = pack_bf16(__uint_as_float(af[1] << 16) * e01.x, __uint_as_float(af[1] & 0xffff0000u) * e01.y);
-                af[2] = pack_bf16(__uint_as_float(af[2] << 16) * e89.x, __uint_as_float(af[2] & 0xffff0000u) * e89.y);
-                af[3] = pack_bf16(__uint_as_float(af[3] << 16) * e89.x, __uint_as_float(af[3] & 0xffff0000u) * e89.y);
+            {   // K~ = K e_j: fragment registers hold tokens j = 16 ks + 2t (+1) and + 8.  One packed bf16 multiply per
+                // register (e_j rounded to bf16 first: one more 2^-9 rounding on W than an fp32 multiply, no visible change in
+                // the parity numbers, a fifth of the instructions)
+                const uint32_t p01 = eB[ks * 8 + t], p89 = eB[ks * 8 + t + 4];
+                asm("mul.rn.bf16x2 %0, %0, %1;" : "+r"(af[0]) : "r"(p01));
+                asm("mul.rn.bf16x2 %0, %0, %1;" : "+r"(af[1]) : "r"(p01));
+                asm("mul.rn.bf16x2 %0, %0, %1;" : "+r"(af[2]) : "r"(p89));
+                asm("mul.rn.bf16x2 %0, %0, %1;" : "+r"(af[3]) : "r"(p89));
             }
             ldmatrix_x4(bf0, aT + sw128_offset(ng * 32 + ((lane >> 4) & 1) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
             ldmatrix_x4(bf1, aT + sw128_offset(ng * 32 + 16 + ((lane >> 4) & 1) * 8 + (lane & 7), ks * 2 + ((lane >> 3) & 1)));
@@ -352,6 +354,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     float* sPost = sOfac + 256;                           // [4] factor applied to S AFTER chunk n's accumulate: gamma | 1
     float* sPre = sPost + 4;                              // [4] factor applied to S BEFORE chunk n's accumulate: 1 | gamma
     float* sFast = sPre + 4;                              // [4] chunk n in slot n & 3
+    uint32_t* sEb = reinterpret_cast<uint32_t*>(sFast + 4);   // [4][32] exp(Gamma_i) as bf16 pairs (tokens 2l, 2l+1): W^T fragment factors
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + kNumBars);
     // work unit of this CTA, written once by thread 0: [0] time segment [1] chain [2] clip [3] head [4] first chunk
@@ -460,7 +463,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             }
         };
         auto scan_chunk = [&](int m, const float (&gv)[2], const float (&bv)[2]) {
-            gate_scan(gv, bv, sBt + (m & 1) * 64, sGam + (m & 1) * 64, sE + (m & 3) * 64, sCj + (m & 1) * 64, sKd + (m & 3) * 64,
+            gate_scan(gv, bv, sBt + (m & 1) * 64, sGam + (m & 1) * 64, sE + (m & 3) * 64, sEb + (m & 3) * 32, sCj + (m & 1) * 64, sKd + (m & 3) * 64,
                       sFast + (m & 3), sOfac + (m & 3) * 64, sPost + (m & 3), sPre + (m & 3), scale, lane);
         };
         float g_nx[2] = {0.f, 0.f}, b_nx[2] = {0.f, 0.f};
@@ -649,6 +652,9 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 PT(24, tid == 256, m);   // wait: staging buffer free + group barrier
                 const float* of = sOfac + (m & 3) * 64 + 2 * (lane & 3);
                 const uint32_t ost_half = sbase + kOffOst + hh * 16384;
+                float2 cf[8];       // the same eight column (token) factors for both lane groups: loaded once
+#pragma unroll
+                for (int q = 0; q < 8; ++q) cf[q] = *reinterpret_cast<const float2*>(of + 8 * q);
 #pragma unroll
                 for (int grp = 0; grp < (ABL(7) ? 0 : 2); ++grp) {
                     uint32_t r[32];
@@ -657,7 +663,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                     uint32_t pk[16];
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float2 c = *reinterpret_cast<const float2*>(of + 8 * q);
+                        const float2 c = cf[q];
                         pk[2 * q] = pack_bf16(__uint_as_float(r[4 * q]) * c.x, __uint_as_float(r[4 * q + 1]) * c.y);
                         pk[2 * q + 1] = pack_bf16(__uint_as_float(r[4 * q + 2]) * c.x, __uint_as_float(r[4 * q + 3]) * c.y);
                     }
@@ -696,7 +702,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 const int sw = (warp - 8);                                          // 0 .. 4 NH - 1
                 for (int u = sw; u < (ABL(4) ? 0 : 8); u += 4 * NH)
                     w_unit_mma(sbase + kOffKq + (uint32_t)(m % 3) * kKqSlotBytes, sbase + kOffTp + st * 8192, smem + kOffWt + st * 8192,
-                               sE + (m & 3) * 64, u & 3, u >> 2, lane);
+                               sEb + (m & 3) * 32, u & 3, u >> 2, lane);
                 fence_proxy_async_smem();
                 mbar_arrive(&bars[kKsideFull + st]);
                 PT(22, tid == 256, m);   // W^T mma.sync
