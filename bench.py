@@ -177,6 +177,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the GPU-local CPUs before allocating host buffers")
     ap.add_argument("--varlen", type=float, default=0.0,
                     help="s > 0: pack the batch and cut it into clips of lengths uniform in [1-s, 1+s] x frames (cu_seqlens call)")
     ap.add_argument("--flags", type=int, default=0, help="GDKVM_FLAG_* forwarded to the op (1=recurrent, 2=chunked, 4=flat, 8=frame chunks, n<<8 = n time segments)")
@@ -208,6 +209,8 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from gdkvm_b200.host import bind_host_to_gpu
+    host_cpus = None if args.no_numa else bind_host_to_gpu(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -308,7 +311,8 @@ def main():
         h2d, d2h = pipe.bytes_per_call()
         e2e = {"value": world * B * W["frames"] / (float(em.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(em.item()),
-               "steps": e2e_steps, "check": "readout matches device-resident run: %s" % bool(torch.equal(ho.to(dev), o))}
+               "steps": e2e_steps, "check": "readout matches device-resident run: %s" % bool(torch.equal(ho.to(dev), o)),
+               "host_cpus_bound": len(host_cpus) if host_cpus else None}
         del hq, hk, hv, hg, hb, hs, ho, hsT, pipe
     clocks = sampler.stop() if sampler is not None else None
 

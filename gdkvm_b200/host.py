@@ -17,6 +17,28 @@ import torch
 from .ops import gdr_lkva_out
 
 
+def bind_host_to_gpu(device_index: int):
+    """Pin the calling process to the CPUs NVML reports as local to ``device_index`` (its NUMA node), so that the pinned
+    host buffers allocated afterwards are first-touched next to the GPU's PCIe root.  With one process per GPU and all
+    buffers on one node, the host->device copies of eight ranks share one memory controller.
+    Returns the CPU list used, or None when NVML / the affinity mask is unavailable or disjoint from the allowed CPUs.
+    """
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, ((os.cpu_count() or 64) + 63) // 64)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        use = local & os.sched_getaffinity(0)
+        if not use:
+            return None
+        os.sched_setaffinity(0, use)
+        return sorted(use)
+    except Exception:
+        return None
+
+
 class _Slot:
     def __init__(self, n, T, H, K, V, io_dtype, gate_dtype, dev, with_s0):
         e = lambda *s, dt: torch.empty(*s, dtype=dt, device=dev)
