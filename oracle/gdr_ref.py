@@ -141,6 +141,27 @@ def gdr_chunk_ref(
     return o, S
 
 
+def gdr_recurrent_varlen_ref(q, k, v, g, beta, cu_seqlens, scale=None, initial_state=None):
+    """Packed variable-length clips (fla's ``cu_seqlens``, fla/ops/gated_delta_rule/chunk.py:375): q,k,v [1,T,H,*], clip n =
+    rows cu_seqlens[n] .. cu_seqlens[n+1]-1, states [N,H,K,V].  One ``gdr_recurrent_ref`` call per clip; a clip without
+    tokens passes its initial state through.  Returns (o [1,T,H,V] fp32, final_state [N,H,K,V] fp32)."""
+    N = len(cu_seqlens) - 1
+    H, K, V = q.shape[2], q.shape[3], v.shape[3]
+    o = torch.zeros(1, q.shape[1], H, V, dtype=torch.float32)
+    sT = torch.zeros(N, H, K, V, dtype=torch.float32)
+    for n in range(N):
+        a, b = int(cu_seqlens[n]), int(cu_seqlens[n + 1])
+        s0 = initial_state[n:n + 1] if initial_state is not None else None
+        if b == a:
+            if s0 is not None:
+                sT[n] = s0[0]
+            continue
+        o_n, s_n = gdr_recurrent_ref(q[:, a:b], k[:, a:b], v[:, a:b], g[:, a:b], beta[:, a:b], scale, s0)
+        o[:, a:b] = o_n
+        sT[n] = s_n[0]
+    return o, sT
+
+
 def make_inputs(B, T, H, K, V, *, seed=1234, frame_tokens=0, correlated=False,
                 dtype=torch.float32, with_state=True):
     """Seeded synthetic inputs of SURVEY.md §8(d) / BASELINE.md §3.

@@ -103,6 +103,33 @@ def test_time_segment_planning(built_lib):
     assert segs(2, 40, 49, 2, V=40, flags=1) == 1                 # recurrent path: no segments
 
 
+def test_varlen_validation_without_gpu(built_lib):
+    """gdkvm_gdr_fwd_varlen checks its arguments before it touches the device: packed layout (B = 1), offset width,
+    offset pointer; with everything valid and no sm_100 device it fails loudly (no CPU path)."""
+    from gdkvm_b200 import _cabi, ops
+    lib = _cabi.load()
+    T, H = 130, 2
+    q = torch.zeros(1, T, H, 64, dtype=torch.bfloat16)
+    v = torch.zeros(1, T, H, 256, dtype=torch.bfloat16)
+    g = torch.zeros(1, T, H)
+    cu = torch.tensor([0, 100, 130], dtype=torch.int64)
+    call = lambda p, ptr, nbytes, n: lib.gdkvm_gdr_fwd_varlen(ctypes.byref(p), ctypes.c_void_p(ptr), nbytes, n, None)
+    p = ops._make_params(q, q, v, g, g, v, None, None, 0.125, 0, 0)
+    assert call(p, 0, 8, 2) == -1                              # NULL offsets
+    assert call(p, cu.data_ptr(), 2, 2) == -3                  # offsets must be 4 or 8 bytes wide
+    assert call(p, cu.data_ptr(), 8, 0) == -3                  # at least one clip
+    assert call(p, cu.data_ptr() + 4, 8, 2) == -5              # misaligned offsets
+    q2 = torch.zeros(2, T, H, 64, dtype=torch.bfloat16)
+    v2 = torch.zeros(2, T, H, 256, dtype=torch.bfloat16)
+    g2 = torch.zeros(2, T, H)
+    p2 = ops._make_params(q2, q2, v2, g2, g2, v2, None, None, 0.125, 0, 0)
+    assert call(p2, cu.data_ptr(), 8, 2) == -3                 # packed clips come as one batch row
+    if not torch.cuda.is_available():
+        assert call(p, cu.data_ptr(), 8, 2) in (-6, -7)        # no sm_100 device: ARCH or CUDA error, never a fallback
+        with pytest.raises((RuntimeError, NotImplementedError)):
+            ops.gdr_lkva_varlen(q, q, v, g, g, cu)
+
+
 def test_fwd_without_gpu_fails_loudly(built_lib):
     """No GPU here: the C entry point must return an error, never compute on the host."""
     if torch.cuda.is_available():

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.gdr_ref import gdr_recurrent_ref, make_inputs, max_rel_err
+from oracle.gdr_ref import gdr_recurrent_ref, gdr_recurrent_varlen_ref, make_inputs, max_rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -318,17 +318,7 @@ def _packed(lens, H, V, seed, dtype=torch.bfloat16, K=64):
 
 
 def _varlen_ref(q, k, v, g, beta, S0, cu):
-    o = torch.zeros(1, q.shape[1], q.shape[2], v.shape[-1])
-    sT = torch.zeros_like(S0)
-    for n in range(len(cu) - 1):
-        a, b = int(cu[n]), int(cu[n + 1])
-        if b == a:
-            sT[n] = S0[n]
-            continue
-        o_n, s_n = gdr_recurrent_ref(q[:, a:b], k[:, a:b], v[:, a:b], g[:, a:b], beta[:, a:b], None, S0[n:n + 1])
-        o[:, a:b] = o_n
-        sT[n] = s_n[0]
-    return o, sT
+    return gdr_recurrent_varlen_ref(q, k, v, g, beta, cu, None, S0)
 
 
 @pytest.mark.parametrize("case", [

@@ -10,7 +10,8 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.gdr_ref import (chunk_schedule, gdr_chunk_ref, gdr_recurrent_ref, make_inputs, max_rel_err)
+from oracle.gdr_ref import (chunk_schedule, gdr_chunk_ref, gdr_recurrent_ref, gdr_recurrent_varlen_ref, make_inputs,
+                            max_rel_err)
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
@@ -143,3 +144,19 @@ def test_linearity_in_values():
     o, S = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
     o2, S2 = gdr_recurrent_ref(q, k, 2 * v, g, beta, None, 2 * S0)
     assert torch.equal(o2, 2 * o) and torch.equal(S2, 2 * S)
+
+
+def test_varlen_oracle_is_the_per_clip_oracle():
+    """Packed clips: equal lengths reproduce the batched oracle exactly; an empty clip passes its state through."""
+    B, T, H, K, V = 3, 40, 2, 16, 24
+    q, k, v, g, beta, S0 = make_inputs(B, T, H, K, V, seed=7)
+    o_b, s_b = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    pk = lambda t: t.reshape(1, B * T, *t.shape[2:])
+    cu = [0, T, 2 * T, 3 * T]
+    o_p, s_p = gdr_recurrent_varlen_ref(pk(q), pk(k), pk(v), pk(g), pk(beta), cu, None, S0)
+    assert torch.equal(o_p.reshape(B, T, H, V), o_b) and torch.equal(s_p, s_b)
+    cu = [0, 25, 25, 3 * T]                      # clip 1 is empty, clips 0 and 2 are ragged
+    o_r, s_r = gdr_recurrent_varlen_ref(pk(q), pk(k), pk(v), pk(g), pk(beta), cu, None, S0)
+    assert torch.equal(s_r[1], S0[1])
+    o0, s0 = gdr_recurrent_ref(pk(q)[:, :25], pk(k)[:, :25], pk(v)[:, :25], pk(g)[:, :25], pk(beta)[:, :25], None, S0[:1])
+    assert torch.equal(o_r[:, :25], o0) and torch.equal(s_r[0], s0[0])
