@@ -20,6 +20,10 @@ RECURRENT, CHUNKED, FLAT, FRAME = 0x1, 0x2, 0x4, 0x8
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
 
+def SEG(n):
+    return (n & 0xF) << 8
+
+
 @pytest.fixture(scope="module")
 def op(built_lib):
     assert torch.cuda.is_available(), "-m gpu tests need a B200"
@@ -232,6 +236,42 @@ def test_chunk_gated_delta_rule_with_qk_l2norm(op):
     assert max_rel_err(o, o_ref) <= 2e-2 and max_rel_err(sT, s_ref) <= 2e-2
 
 
+@pytest.mark.parametrize("case", [
+    # B, T, H, V, frame_tokens, flags, gate multiplier on tokens 64..191
+    (2, 5 * 49, 3, 256, 49, 0, 1.0),
+    (2, 4 * 64 + 30, 2, 128, 0, SEG(2), 1.0),
+    (2, 5 * 64, 2, 256, 0, 0, 300.0),            # chunks 1-2 take the slow (per-element decay) path
+])
+def test_qk_l2norm_with_wide_norm_spread(op, case):
+    """use_qk_l2norm_in_kernel=True with un-normalised q, k whose row norms spread over several decades: the
+    normalisation pass + the op against the oracle on fp32-normalised inputs."""
+    B, T, H, V, C, fl, gmul = case
+    q, k, v, g, beta, S0 = make_inputs(B, T, H, 64, V, seed=61, frame_tokens=C, correlated=(C == 49), dtype=torch.bfloat16)
+    gen = torch.Generator().manual_seed(62)
+    amp = lambda t: (t.float() * torch.exp(2.3 * torch.randn(B, T, H, 1, generator=gen))).bfloat16()
+    q, k = amp(q), amp(k)
+    g = g.clone()
+    g[:, 64:192] *= gmul
+    l2 = lambda t: t.float() * torch.rsqrt((t.float() ** 2).sum(-1, keepdim=True) + 1e-6)
+    o_ref, s_ref = gdr_recurrent_ref(l2(q).bfloat16(), l2(k).bfloat16(), v, g, beta, None, S0)
+    qd, kd, vd, gd, bd, sd = _dev(q, k, v, g, beta, S0)
+    o, sT = op.chunk_gated_delta_rule(qd, kd, vd, gd, bd, initial_state=sd, output_final_state=True, frame_tokens=C,
+                                      flags=CHUNKED | fl, use_qk_l2norm_in_kernel=True)
+    assert max_rel_err(o, o_ref) <= 2e-2 and max_rel_err(sT, s_ref) <= 2e-2
+
+
+def test_qk_l2norm_packed_clips(op):
+    lens = [200, 64, 1, 333, 17]
+    q, k, v, g, beta, S0, cu = _packed(lens, 2, 256, 63)
+    q, k = (q.float() * 3.0).bfloat16(), (k.float() * 0.2).bfloat16()
+    l2 = lambda t: t.float() * torch.rsqrt((t.float() ** 2).sum(-1, keepdim=True) + 1e-6)
+    o_ref, s_ref = gdr_recurrent_varlen_ref(l2(q).bfloat16(), l2(k).bfloat16(), v, g, beta, cu, None, S0)
+    qd, kd, vd, gd, bd, sd = _dev(q, k, v, g, beta, S0)
+    o, sT = op.chunk_gated_delta_rule(qd, kd, vd, gd, bd, initial_state=sd, output_final_state=True, cu_seqlens=cu.cuda(),
+                                      use_qk_l2norm_in_kernel=True)
+    assert max_rel_err(o.float().cpu(), o_ref) <= 2e-2 and max_rel_err(sT.cpu(), s_ref) <= 2e-2
+
+
 def test_kat_on_device(op):
     """Orthonormal keys, g=0, beta=1: S = sum k_i v_i^T exactly; reading q=k_j returns scale*v_j."""
     K, V = 64, 64
@@ -263,10 +303,6 @@ def test_host_pipeline_matches_device_call(op):
 
 
 # ---------------- full-size (BASELINE configs[1]) properties ----------------
-
-def SEG(n):
-    return (n & 0xF) << 8
-
 
 @pytest.mark.parametrize("shape", [
     # B, T, H, V, frame_tokens, flags
