@@ -1162,7 +1162,9 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
     const int chains = p.B * p.H, cpf = (C + 63) / 64, nc = F * cpf;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
-    int nseg = cap != cudaStreamCaptureStatusNone ? 1 : chunked_segments(p, device_sm_count());
+    // under capture: uncut unless the caller asks for segments explicitly (the scratch then becomes alloc / free nodes of the graph)
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
+    int nseg = (capturing && ((p.flags >> 8) & 0xfu) == 0) ? 1 : chunked_segments(p, device_sm_count());
     int seg_chunks = (nc + nseg - 1) / nseg;
     float* xstate = nullptr;
     int* xsync = nullptr;
@@ -1201,11 +1203,6 @@ int chunked_varlen_seg_chunks(const GdkvmGdrParams& p, int nseq, int sms) {
 int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream) {
     const int ae = ensure_smem_attr();
     if (ae != 0) return ae;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
-        (void)cudaGetLastError();
-        return (int)cudaErrorStreamCaptureUnsupported;              // needs a per-launch workspace
-    }
     CUtensorMap mq, mk, mv, mo;
     const int me = make_maps(p, p.T, 1, &mq, &mk, &mv, &mo);
     if (me != 0) return me;

@@ -57,7 +57,9 @@ enum GdkvmStatus {
                                         /* chunked kernel: cut every chain into n (1..15) time
                                            segments scheduled as separate work units (fills the
                                            ragged last wave of chains over SMs; bit-identical
-                                           results).  0 = let the library choose                      */
+                                           results).  0 = let the library choose (a launch under
+                                           stream capture is then left uncut; with an explicit n the
+                                           hand-off scratch becomes alloc / free nodes of the graph)  */
 
 /*
  * One forward call of the memory module over a batch of clips.
@@ -121,8 +123,8 @@ int gdkvm_gdr_fwd(const GdkvmGdrParams* params, void* cuda_stream);
  * non-decreasing), an array of n_seqs+1 offsets in DEVICE memory of cu_seqlens_bytes (4 or 8) bytes each -- the
  * library never reads it on the host, so the call stays asynchronous.  initial_state / final_state are
  * [n_seqs, H, K, V]; a clip without tokens passes its initial state through.  frame_tokens is ignored (flat 64-token
- * tiling; token-causal semantics make that exactly equivalent).  Uses a stream-ordered per-launch workspace, so it
- * cannot be captured into a CUDA graph (GDKVM_ERR_CUDA, cudaErrorStreamCaptureUnsupported).
+ * tiling; token-causal semantics make that exactly equivalent).  Uses a stream-ordered per-launch workspace
+ * (cudaMallocAsync / cudaFreeAsync on cuda_stream); under stream capture these become allocation / free nodes of the graph.
  */
 int gdkvm_gdr_fwd_varlen(const GdkvmGdrParams* params, const void* cu_seqlens, int32_t cu_seqlens_bytes, int32_t n_seqs,
                          void* cuda_stream);

@@ -195,6 +195,31 @@ def test_cuda_graph_capture_and_two_streams(op):
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(o, o_ref) and torch.equal(sT, s_ref)
+    # explicit time segments inside a graph: the hand-off scratch becomes allocation / free nodes of the graph
+    g2 = torch.cuda.CUDAGraph()
+    o.zero_(); sT.zero_()
+    with torch.cuda.graph(g2):
+        op.gdr_lkva_out(q, k, v, g, beta, o, sT, None, S0, 49, SEG(2))
+    for _ in range(3):
+        o.zero_(); sT.zero_()
+        g2.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(o, o_ref) and torch.equal(sT, s_ref)
+    # packed variable-length clips inside a graph (unit table, scratch and flags are nodes of the graph)
+    lens = [70, 3, 129]
+    qp, kp, vp, gp, bp, Sp, cu = _packed(lens, 2, 256, 36)
+    qp, kp, vp, gp, bp, Sp = _dev(qp, kp, vp, gp, bp, Sp)
+    cud = cu.cuda()
+    ov_ref, sv_ref = op.gdr_lkva_varlen(qp, kp, vp, gp, bp, cud, None, Sp, True, CHUNKED)
+    torch.cuda.synchronize()
+    g3 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g3):
+        ov, sv = op.gdr_lkva_varlen(qp, kp, vp, gp, bp, cud, None, Sp, True, CHUNKED)
+    for _ in range(2):
+        ov.zero_(); sv.zero_()
+        g3.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(ov, ov_ref) and torch.equal(sv, sv_ref)
     # two streams, two different problems, launched back to back
     q2, k2, v2, g2, b2, S2 = _dev(*make_inputs(2, 5 * 64, 3, 64, 128, seed=35, dtype=torch.bfloat16))
     o2_ref, s2_ref = op.gdr_lkva(q2, k2, v2, g2, b2, None, S2, True, 0)
