@@ -963,6 +963,13 @@ int pick_segments(int chains, int nc, int sms) {
     return best;
 }
 
+bool device_has_mempools() {
+    int dev = 0, ok = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, dev) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return ok != 0;
+}
+
 int device_sm_count() {
     static std::mutex mu;
     static int cached[64];
@@ -1162,9 +1169,10 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
     const int chains = p.B * p.H, cpf = (C + 63) / 64, nc = F * cpf;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
-    // under capture: uncut unless the caller asks for segments explicitly (the scratch then becomes alloc / free nodes of the graph)
+    // under capture the scratch becomes allocation / free nodes of the graph (stream-ordered allocator); without memory-pool
+    // support a captured launch stays uncut
     const bool capturing = cap != cudaStreamCaptureStatusNone;
-    int nseg = (capturing && ((p.flags >> 8) & 0xfu) == 0) ? 1 : chunked_segments(p, device_sm_count());
+    int nseg = (capturing && !device_has_mempools()) ? 1 : chunked_segments(p, device_sm_count());
     int seg_chunks = (nc + nseg - 1) / nseg;
     float* xstate = nullptr;
     int* xsync = nullptr;

@@ -57,9 +57,9 @@ enum GdkvmStatus {
                                         /* chunked kernel: cut every chain into n (1..15) time
                                            segments scheduled as separate work units (fills the
                                            ragged last wave of chains over SMs; bit-identical
-                                           results).  0 = let the library choose (a launch under
-                                           stream capture is then left uncut; with an explicit n the
-                                           hand-off scratch becomes alloc / free nodes of the graph)  */
+                                           results).  0 = let the library choose.  Under stream
+                                           capture the hand-off scratch becomes alloc / free nodes of
+                                           the graph                                                  */
 
 /*
  * One forward call of the memory module over a batch of clips.

@@ -195,7 +195,8 @@ def test_cuda_graph_capture_and_two_streams(op):
         graph.replay()
         torch.cuda.synchronize()
         assert torch.equal(o, o_ref) and torch.equal(sT, s_ref)
-    # explicit time segments inside a graph: the hand-off scratch becomes allocation / free nodes of the graph
+    # time segments inside a graph (explicit, and the library's own choice on a shape it cuts): the hand-off scratch becomes
+    # allocation / free nodes of the graph
     g2 = torch.cuda.CUDAGraph()
     o.zero_(); sT.zero_()
     with torch.cuda.graph(g2):
@@ -205,6 +206,19 @@ def test_cuda_graph_capture_and_two_streams(op):
         g2.replay()
         torch.cuda.synchronize()
         assert torch.equal(o, o_ref) and torch.equal(sT, s_ref)
+    qb, kb, vb, gb, bb, Sb = _dev(*make_inputs(19, 24 * 64, 8, 64, 256, seed=37, dtype=torch.bfloat16))   # 152 chains: cut
+    assert op.plan_segments(qb, kb, vb, gb, bb) > 1
+    ob_ref, sb_ref = op.gdr_lkva(qb, kb, vb, gb, bb, None, Sb, True, 0, SEG(1))
+    ob, sb2 = torch.zeros_like(ob_ref), torch.zeros_like(sb_ref)
+    torch.cuda.synchronize()
+    g4 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g4):
+        op.gdr_lkva_out(qb, kb, vb, gb, bb, ob, sb2, None, Sb, 0, 0)
+    for _ in range(2):
+        ob.zero_(); sb2.zero_()
+        g4.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(ob, ob_ref) and torch.equal(sb2, sb_ref)
     # packed variable-length clips inside a graph (unit table, scratch and flags are nodes of the graph)
     lens = [70, 3, 129]
     qp, kp, vp, gp, bp, Sp, cu = _packed(lens, 2, 256, 36)
