@@ -256,9 +256,10 @@ __device__ __forceinline__ void w_unit_mma(uint32_t aK, uint32_t aT, uint8_t* wt
 // Rows 0 .. valid-1 of one value half of the readout staging tile ([2 value blocks][64 tokens][64] bf16, 128B swizzle)
 // -> global memory with 16-byte stores, by the 128 threads of a state warpgroup.  Out of line on purpose: it runs once
 // per clip and must not add to the register pressure of the readout it is called from.
-__device__ __noinline__ void store_valid_rows(const uint8_t* stage, __nv_bfloat16* og, int64_t row_stride, int valid, int stid) {
+__device__ __noinline__ void store_valid_rows(const uint8_t* stage, __nv_bfloat16* og, int64_t row_stride, int valid, int stid, int nblk) {
     for (int idx = stid; idx < valid * 16; idx += 128) {
         const int row = idx >> 4, blk = (idx >> 3) & 1, ck = idx & 7;
+        if (blk >= nblk) continue;
         const uint4 val = *reinterpret_cast<const uint4*>(stage + blk * 8192 + sw128_offset(row, ck));
         *reinterpret_cast<uint4*>(og + (int64_t)row * row_stride + blk * 64 + ck * 8) = val;
     }
@@ -352,7 +353,9 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     volatile int* s_info = reinterpret_cast<volatile int*>(s_tmem + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int V = p.V, NH = V >> 7, VB = V >> 6;
+    // V = 64: one state warpgroup whose upper 64 TMEM lanes idle on zeros (the second value block of the V ring is never loaded)
+    const int V = p.V, NH = V > 128 ? 2 : 1, VB = V >> 6;
+    const uint32_t v_tile_bytes = V >= 128 ? 16384u : 8192u;
     const int cpf = (C + 63) >> 6;
     const float scale = p.scale;
 
@@ -393,6 +396,10 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     for (int i = tid; i < 1536; i += kThreads) {
         if (i < 1024) reinterpret_cast<uint4*>(smem + kOffPp)[i] = make_uint4(0u, 0u, 0u, 0u);
         else reinterpret_cast<uint4*>(smem + kOffH)[i - 1024] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (V < 128) {      // the value block that is never loaded feeds the idle upper TMEM lanes: keep it zero
+        for (int i = tid; i < 1024; i += kThreads)
+            reinterpret_cast<uint4*>(smem + kOffV + (i >> 9) * kVSlotBytes + 8192)[i & 511] = make_uint4(0u, 0u, 0u, 0u);
     }
     fence_proxy_async_smem();
     if (warp == 16) {
@@ -607,7 +614,8 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             {   // initial state -> TMEM: the caller's for the first segment, the previous segment's hand-off otherwise
                 uint32_t r[32];
                 const int chain = U_CHAIN, seg = U_SEG;
-                const float* s0 = p.initial_state ? p.initial_state + (int64_t)chain * 64 * V + vcol : nullptr;
+                const bool col_ok = vcol < V;                 // V = 64: lanes 64-127 carry zeros
+                const float* s0 = (p.initial_state && col_ok) ? p.initial_state + (int64_t)chain * 64 * V + vcol : nullptr;
                 if (seg != 0) {
                     if (stid == 0) {
                         const int* flag = xsync + 1 + chain * 2 + hh;
@@ -618,7 +626,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                         }
                     }
                     named_bar_sync(bar_id, 128);
-                    s0 = xstate + (int64_t)chain * 64 * V + vcol;
+                    s0 = col_ok ? xstate + (int64_t)chain * 64 * V + vcol : nullptr;
                 }
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -675,7 +683,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                     store_valid_rows(smem + kOffOst + hh * 16384,
                                      reinterpret_cast<__nv_bfloat16*>(p.o) + ((int64_t)s_info[4] + (m << 6)) * p.o_stride[1] +
                                          (int64_t)s_info[3] * p.o_stride[2] + hh * 128,
-                                     p.o_stride[1], (int)s_info[6] - (m << 6), stid);
+                                     p.o_stride[1], (int)s_info[6] - (m << 6), stid, V >= 128 ? 2 : 1);
                 } else if (stid == 0) {
                     int c0, f;
                     chunk_coord(m, c0, f);
@@ -780,7 +788,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             const int chain = U_CHAIN, seg = U_SEG;
             const bool last_seg = s_info[7] != 0;
             float* sT = last_seg ? p.final_state : xstate;       // the caller's final state | hand-off to the next segment
-            if (sT != nullptr) {
+            if (sT != nullptr && vcol < V) {
                 uint32_t r[32];
                 const float post = sPost[(NC - 1) & 3];
                 sT += (int64_t)chain * 64 * V + vcol;
@@ -827,7 +835,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                     chunk_coord(m, c0, f);
                     for (int hh = 0; hh < NH; ++hh) {
                         uint64_t* vb = &bars[kVTile + m * 2 + hh];
-                        mbar_arrive_expect_tx(vb, 16384u);
+                        mbar_arrive_expect_tx(vb, v_tile_bytes);
                         tma_load_5d(smem + kOffV + m * kVSlotBytes + hh * 16384, &mv, vb, 0, c0, h * VB + hh * 2, f, b);
                     }
                 }
@@ -896,7 +904,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                         int c0, f;
                         chunk_coord(n + 2, c0, f);
                         uint64_t* vb = &bars[kVTile + st * 2 + hh];
-                        mbar_arrive_expect_tx(vb, 16384u);
+                        mbar_arrive_expect_tx(vb, v_tile_bytes);
                         tma_load_5d(smem + kOffV + st * kVSlotBytes + hh * 16384, &mv, vb, 0, c0, hv, f, b);
                     }
                     __syncwarp();
@@ -1016,7 +1024,7 @@ namespace gdkvm {
 #endif
 
 bool chunked_supports(const GdkvmGdrParams& p) {
-    if (p.io_dtype != GDKVM_BF16 || p.K != 64 || (p.V != 128 && p.V != 256) || p.T <= 0) return false;
+    if (p.io_dtype != GDKVM_BF16 || p.K != 64 || (p.V != 64 && p.V != 128 && p.V != 256) || p.T <= 0) return false;
     // TMA: 16-byte aligned bases and strides; the value/readout head stride must equal V so that
     // (head, 64-wide value block) folds into one tensor-map dimension.
     const void* ptrs[4] = {p.q, p.k, p.v, p.o};
@@ -1071,7 +1079,7 @@ int make_maps(const GdkvmGdrParams& p, int C, int F, CUtensorMap* mq, CUtensorMa
     }
     {
         const uint64_t dims[5] = {64, (uint64_t)C, H * (V / 64), (uint64_t)F, B};
-        const uint32_t box[5] = {64, 64, 2, 1, 1};
+        const uint32_t box[5] = {64, 64, V >= 128 ? 2u : 1u, 1, 1};     // V = 64: one value block per head
         const uint64_t sv[4] = {(uint64_t)p.v_stride[1] * 2, 128, (uint64_t)p.v_stride[1] * 2 * C, (uint64_t)p.v_stride[0] * 2};
         const uint64_t so[4] = {(uint64_t)p.o_stride[1] * 2, 128, (uint64_t)p.o_stride[1] * 2 * C, (uint64_t)p.o_stride[0] * 2};
         int rc = make_tmap(mv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, p.v, dims, sv, box, CU_TENSOR_MAP_SWIZZLE_128B);

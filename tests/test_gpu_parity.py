@@ -60,6 +60,7 @@ def _paths(op, q, k, v, g, beta, C):
     (1, 37, 1, 32, 40, 0, False),            # K=32, V not a multiple of anything
     (1, 70, 2, 128, 128, 0, False),          # K=128
     (3, 1, 2, 64, 64, 0, False),             # single token
+    (2, 5 * 49 + 13, 3, 64, 64, 0, True),    # V = 64: the chunk kernel with the upper TMEM lanes idle
 ])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
 def test_parity_vs_oracle(op, shape, dtype):
@@ -442,6 +443,23 @@ def test_varlen_many_short_clips(op, c_oracle):
             continue
         o_ref, s_ref = c_oracle.gdr_recurrent_c(q[:, a:b], k[:, a:b], v[:, a:b], g[:, a:b], beta[:, a:b], None, S0[n:n + 1])
         assert max_rel_err(o[:, a:b].float().cpu(), o_ref) <= 2e-2 and max_rel_err(sT[n:n + 1].cpu(), s_ref) <= 2e-2, n
+
+
+def test_v64_on_the_chunk_kernel(op):
+    """d_v = 64 per head: tcgen05 path (one value block per head, nothing written into the neighbouring head), frame-aligned
+    and flat tiling, time segments, packed clips -- against the fp32-exact recurrent kernel and the oracle."""
+    q, k, v, g, beta, S0 = make_inputs(2, 6 * 64, 3, 64, 64, seed=71, frame_tokens=64, dtype=torch.bfloat16)
+    assert op.plan(q.cuda(), k.cuda(), v.cuda(), g.cuda(), beta.cuda()) == 1
+    o_ref, s_ref = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    for fl in (CHUNKED, CHUNKED | FRAME, CHUNKED | SEG(3)):
+        o, sT = _run(op, q, k, v, g, beta, S0, frame_tokens=64, flags=fl)
+        assert max_rel_err(o, o_ref) <= 2e-2 and max_rel_err(sT, s_ref) <= 2e-2, fl
+    lens = [100, 64, 7, 200]
+    qp, kp, vp, gp, bp, Sp, cu = _packed(lens, 3, 64, 72)
+    ov_ref, sv_ref = gdr_recurrent_varlen_ref(qp, kp, vp, gp, bp, cu, None, Sp)
+    qd, kd, vd, gd, bd, sd = _dev(qp, kp, vp, gp, bp, Sp)
+    ov, sv = op.gdr_lkva_varlen(qd, kd, vd, gd, bd, cu.cuda(), None, sd, True, CHUNKED)
+    assert max_rel_err(ov.float().cpu(), ov_ref) <= 2e-2 and max_rel_err(sv.cpu(), sv_ref) <= 2e-2
 
 
 def test_varlen_equals_batched_call_bit_for_bit(op):
