@@ -352,6 +352,17 @@ def main():
                 "traffic": recorded_traffic(), "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
                 "kernel": "gdr_chunk_kernel (tcgen05)" if plan == 1 else "gdr_recurrent_kernel (fp32 CUDA cores)",
                 "frac_of_nominal_8TBs": achieved / 8000.0}
+    if plan == 1:
+        # the secondary (tensor) bound, SURVEY.md section 8(d): 44 executed tcgen05 MMAs of 128 x 64 x 16 per 64-token chunk and
+        # 256-column chain (22 per 128-column value half) against the measured dense bf16 rate
+        chunks = B * H * ((T + 63) // 64 if (C % 64 != 0 or C <= 0) else (T // C) * (C // 64))
+        tf = chunks * 22 * max(1, V // 128) * 2 * 128 * 64 * 16 / (ms_step * 1e-3) / 1e12
+        try:
+            tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:
+            tpeak = 2250.0
+        roofline["tensor_secondary"] = {"executed_TFLOPs": tf, "peak": tpeak, "frac": tf / tpeak,
+                                        "algorithmic_TFLOPs": B * T * H * 6 * K * V / (ms_step * 1e-3) / 1e12}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
