@@ -30,6 +30,25 @@ def chain_partition(B: int, H: int, world: int, rank: int) -> Tuple[slice, slice
     return slice(rank // rpc, rank // rpc + 1), slice((rank % rpc) * hb, (rank % rpc + 1) * hb)
 
 
+def packed_partition(cu_seqlens, world: int, rank: int) -> Tuple[slice, slice]:
+    """(clip slice, token slice) of packed variable-length clips owned by ``rank``: contiguous blocks of whole clips whose
+    token counts are as even as a prefix split allows (a clip is never cut: its chains are sequential in time).  The rank
+    runs ``gdr_lkva_varlen`` on ``q[:, tokens]`` with ``cu_seqlens[clips.start : clips.stop + 1] - cu_seqlens[clips.start]``;
+    no collective is needed.  ``cu_seqlens``: host sequence of N + 1 offsets."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    cu = [int(x) for x in cu_seqlens]
+    n, total = len(cu) - 1, cu[-1]
+    bounds = [0]
+    for r in range(1, world):                    # clip boundary closest to r / world of the tokens, monotone
+        target = total * r / world
+        j = min(range(bounds[-1], n + 1), key=lambda i: (abs(cu[i] - target), i))
+        bounds.append(j)
+    bounds.append(n)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    return slice(lo, hi), slice(cu[lo], cu[hi])
+
+
 def gather_readout(o_local: torch.Tensor, group=None) -> torch.Tensor:
     """All-gather the per-rank readout [B_r,T,H,V] along the clip dimension (equal B_r per rank)."""
     world = dist.get_world_size(group)

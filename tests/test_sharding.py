@@ -23,6 +23,37 @@ def test_chain_partition_covers_everything():
         chain_partition(3, 8, 8, 0)
 
 
+def test_packed_partition_whole_clips_balanced_tokens():
+    from gdkvm_b200.sharding import packed_partition
+    from oracle.gdr_ref import gdr_recurrent_varlen_ref, make_inputs
+    lens = [50, 7, 120, 0, 33, 64, 90, 5]
+    cu = [0]
+    for x in lens:
+        cu.append(cu[-1] + x)
+    for world in (1, 2, 3, 4, 8):
+        clips_seen, toks = [], 0
+        for r in range(world):
+            cs, ts = packed_partition(cu, world, r)
+            clips_seen += list(range(cs.start, cs.stop))
+            assert ts.start == cu[cs.start] and ts.stop == cu[cs.stop]
+            toks += ts.stop - ts.start
+        assert clips_seen == list(range(len(lens))) and toks == cu[-1]
+    cs0, ts0 = packed_partition(cu, 2, 0)
+    assert abs((ts0.stop - ts0.start) - cu[-1] / 2) <= max(lens) / 2
+    # the shards reproduce the unsharded result (the checker stands in for the GPU op)
+    H, K, V = 2, 16, 8
+    q, k, v, g, beta, _ = make_inputs(1, cu[-1], H, K, V, seed=22)
+    S0 = 0.1 * torch.randn(len(lens), H, K, V, generator=torch.Generator().manual_seed(23))
+    o_ref, s_ref = gdr_recurrent_varlen_ref(q, k, v, g, beta, cu, None, S0)
+    for r in range(3):
+        cs, ts = packed_partition(cu, 3, r)
+        cu_r = [c - cu[cs.start] for c in cu[cs.start:cs.stop + 1]]
+        o_r, s_r = gdr_recurrent_varlen_ref(q[:, ts], k[:, ts], v[:, ts], g[:, ts], beta[:, ts], cu_r, None, S0[cs])
+        assert torch.equal(o_r, o_ref[:, ts]) and torch.equal(s_r, s_ref[cs])
+    with pytest.raises(ValueError):
+        packed_partition(cu, 2, 2)
+
+
 def _worker(rank, world, port, tmp):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
