@@ -141,6 +141,34 @@ def gdr_chunk_ref(
     return o, S
 
 
+def gdr_backward_ref(q, k, v, g, beta, do, dsT=None, scale=None, initial_state=None, dtype=torch.float64):
+    """Gradients of the token recurrence by reverse-mode differentiation of the same four lines (ground truth for the
+    backward pass, SURVEY.md section 8f rank 1 -- not built yet; this is the checker it will be held to).
+
+    ``do`` [B,T,H,V] and ``dsT`` [B,H,K,V] (optional) are the cotangents of the readout and of the final state.  Returns
+    ``(dq, dk, dv, dg, dbeta, dS0)`` in ``dtype`` (float64 by default: the recurrence is re-run in that precision).
+    """
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    if scale is None:
+        scale = 1.0 / math.sqrt(K)
+    leaf = lambda x: x.detach().to("cpu", dtype).clone().requires_grad_(True)
+    q_, k_, v_, g_, b_ = map(leaf, (q, k, v, g, beta))
+    S0 = leaf(initial_state) if initial_state is not None else torch.zeros(B, H, K, V, dtype=dtype, requires_grad=True)
+    S, outs = S0, []
+    for i in range(T):
+        k_i = k_[:, i]
+        S = S * g_[:, i].exp()[..., None, None]
+        r = v_[:, i] - torch.einsum("bhkv,bhk->bhv", S, k_i)
+        S = S + k_i[..., :, None] * (b_[:, i][..., None] * r)[..., None, :]
+        outs.append(float(scale) * torch.einsum("bhkv,bhk->bhv", S, q_[:, i]))
+    o = torch.stack(outs, 1)
+    loss = (o * do.detach().to("cpu", dtype)).sum()
+    if dsT is not None:
+        loss = loss + (S * dsT.detach().to("cpu", dtype)).sum()
+    return torch.autograd.grad(loss, (q_, k_, v_, g_, b_, S0))
+
+
 def gdr_recurrent_varlen_ref(q, k, v, g, beta, cu_seqlens, scale=None, initial_state=None):
     """Packed variable-length clips (fla's ``cu_seqlens``, fla/ops/gated_delta_rule/chunk.py:375): q,k,v [1,T,H,*], clip n =
     rows cu_seqlens[n] .. cu_seqlens[n+1]-1, states [N,H,K,V].  One ``gdr_recurrent_ref`` call per clip; a clip without

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.gdr_ref import (chunk_schedule, gdr_chunk_ref, gdr_recurrent_ref, gdr_recurrent_varlen_ref, make_inputs,
+from oracle.gdr_ref import (chunk_schedule, gdr_backward_ref, gdr_chunk_ref, gdr_recurrent_ref, gdr_recurrent_varlen_ref, make_inputs,
                             max_rel_err)
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
@@ -160,3 +160,34 @@ def test_varlen_oracle_is_the_per_clip_oracle():
     assert torch.equal(s_r[1], S0[1])
     o0, s0 = gdr_recurrent_ref(pk(q)[:, :25], pk(k)[:, :25], pk(v)[:, :25], pk(g)[:, :25], pk(beta)[:, :25], None, S0[:1])
     assert torch.equal(o_r[:, :25], o0) and torch.equal(s_r[0], s0[0])
+
+
+def test_backward_oracle_against_finite_differences():
+    """gdr_backward_ref (the checker a backward kernel will be held to): directional derivatives of
+    <do, o> + <dsT, S_T> by central differences in float64."""
+    B, T, H, K, V = 2, 9, 2, 4, 5
+    q, k, v, g, beta, S0 = (t.double() for t in make_inputs(B, T, H, K, V, seed=31))
+    gen = torch.Generator().manual_seed(32)
+    do = torch.randn(B, T, H, V, generator=gen, dtype=torch.float64)
+    dsT = torch.randn(B, H, K, V, generator=gen, dtype=torch.float64)
+    grads = gdr_backward_ref(q, k, v, g, beta, do, dsT, None, S0)
+
+    def loss(q, k, v, g, beta, S0):
+        S = S0.clone()
+        tot = 0.0
+        for i in range(T):
+            S = S * g[:, i].exp()[..., None, None]
+            r = v[:, i] - torch.einsum("bhkv,bhk->bhv", S, k[:, i])
+            S = S + k[:, i][..., :, None] * (beta[:, i][..., None] * r)[..., None, :]
+            tot = tot + (K ** -0.5 * torch.einsum("bhkv,bhk->bhv", S, q[:, i]) * do[:, i]).sum()
+        return tot + (S * dsT).sum()
+
+    args = [q, k, v, g, beta, S0]
+    for idx, gr in enumerate(grads):
+        d = torch.randn(args[idx].shape, generator=gen, dtype=torch.float64)
+        eps = 1e-6
+        plus = [a + eps * d if j == idx else a for j, a in enumerate(args)]
+        minus = [a - eps * d if j == idx else a for j, a in enumerate(args)]
+        fd = (loss(*plus) - loss(*minus)) / (2 * eps)
+        an = (gr * d).sum()
+        assert abs(fd - an) <= 1e-6 * max(1.0, abs(an)), (idx, float(fd), float(an))
