@@ -65,24 +65,29 @@ def recorded_traffic():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md's clocks line + a timestamp), ONE sampler for the whole run at
+    50 ms; every timed region reports the samples that fall inside its own wall-clock window."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.rows = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        """Stop sampling and parse: rows of (epoch seconds, sm MHz, max sm MHz, power W, {reasons})."""
+        if self.rows is not None:
+            return
+        self.rows = []
         if self.p is None:
-            return out
+            return
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -90,23 +95,32 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        import datetime
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                sm, mx = float(c[2]), float(c[3])
+                pw = float(c[4]) if c[4].replace(".", "", 1).isdigit() else None
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.rows.append((ts, sm, mx, pw, {n for n, v in zip(names, c[6:10]) if v.lower().startswith("active")}))
         self.f.close()
         os.unlink(self.f.name)
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+    def window(self, t0, t1):
+        """{"sm_mhz": median, "sm_max_mhz", "reasons", "samples", "power_w_max"} of the samples with t0 <= t <= t1."""
+        self.stop()
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(rows), "seconds": round(t1 - t0, 3)}
+        if rows:
+            sm = sorted(r[1] for r in rows)
+            out.update(sm_mhz=sm[len(sm) // 2], sm_min_mhz=sm[0], sm_max_mhz=max(r[2] for r in rows),
+                       reasons=sorted(set().union(*(r[4] for r in rows))),
+                       power_w_max=max((r[3] for r in rows if r[3] is not None), default=None))
         return out
 
 
@@ -171,6 +185,146 @@ def run_reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def time_steps(fn, steps, barrier=None):
+    """ms per step of `steps` back-to-back calls, CUDA events on the current stream, sync (and barrier) on both sides."""
+    (barrier or torch.cuda.synchronize)()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    (barrier or torch.cuda.synchronize)()
+    return e0.elapsed_time(e1) / steps
+
+
+def time_for(fn, seconds, warmup=3, min_steps=5, barrier=None):
+    """Run `fn` back to back for about `seconds` (after `warmup` calls): (ms per step, steps, wall-clock window)."""
+    for _ in range(warmup):
+        fn()
+    t_w0 = time.time()
+    probe = time_steps(fn, min_steps, barrier)
+    steps = max(min_steps, int(seconds * 1e3 / max(probe, 1e-3)))
+    ms = time_steps(fn, steps, barrier)
+    return ms, steps, (t_w0, time.time())
+
+
+def extra_line(B, T, H, K, V, frames, ms, steps, window, sampler, note=None, abytes=None):
+    abytes = algorithmic_bytes(B, T, H, K, V) if abytes is None else abytes
+    peak, _ = measured_peak_gbs()
+    ach = abytes / (ms * 1e-3) / 1e9
+    out = {"ms_per_step": ms, "steps": steps, "value": B * frames / (ms * 1e-3), "unit": UNIT,
+           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "algorithmic_bytes_per_step": abytes},
+           "clocks": sampler.window(*window) if sampler is not None else None}
+    if note:
+        out["note"] = note
+    return out
+
+
+def fla_child():
+    """--fla-child: flash-linear-attention's Triton chunk_gated_delta_rule on configs[1]'s inputs (own process: Triton's
+    compile time and allocator stay out of the bench process).  Informational comparator, never a dependency."""
+    W = WORKLOADS["echonet_batch"]
+    dev = torch.device("cuda", 0)
+    B, H, K, V, C = W["clips"], W["heads"], W["d_k"], W["d_v"], W["frame_tokens"]
+    T = W["frames"] * C
+    q, k, v, g, beta, S0 = make_device_inputs(B, T, H, K, V, 1234, dev)
+    import warnings
+    warnings.simplefilter("ignore")
+    from fla.ops.gated_delta_rule import chunk_gated_delta_rule as fla_op
+    fn = lambda: fla_op(q, k, v, g, beta, initial_state=S0, output_final_state=True)
+    t0 = time.time()
+    ms, steps, win = time_for(fn, 0.6)
+    print(json.dumps({"ms_per_step": ms, "steps": steps, "value": B * W["frames"] / (ms * 1e-3), "window": win,
+                      "compile_and_run_s": time.time() - t0}), flush=True)
+
+
+def run_extras(args, dev, sampler, main_inputs, main_ms):
+    """Rank 0, one GPU: the other BASELINE configs and comparators, each with its own timing, roofline fraction and the
+    clock samples of its own window.  None of them can break the contract line: failures are reported in place."""
+    import gdkvm_b200
+    extra = {}
+    q, k, v, g, beta, S0 = main_inputs
+    W1 = WORKLOADS["echonet_batch"]
+
+    def guarded(name, fn):
+        try:
+            extra[name] = fn()
+        except Exception as ex:  # noqa: BLE001
+            extra[name] = {"failed": repr(ex)[:300]}
+        torch.cuda.synchronize()
+
+    def camus():
+        W = WORKLOADS["camus"]
+        B, H, K, V, C = W["clips"], W["heads"], W["d_k"], W["d_v"], W["frame_tokens"]
+        T = W["frames"] * C
+        q2, k2, v2, g2, b2, s2 = make_device_inputs(B, T, H, K, V, 2222, dev)
+        o2 = torch.empty(B, T, H, V, dtype=torch.bfloat16, device=dev)
+        sT2 = torch.empty(B, H, K, V, dtype=torch.float32, device=dev)
+        fn = lambda: gdkvm_b200.gdr_lkva_out(q2, k2, v2, g2, b2, o2, sT2, None, s2, C, 0)
+        ms, steps, win = time_for(fn, args.extra_seconds)
+        return extra_line(B, T, H, K, V, W["frames"], ms, steps, win, sampler,
+                          "BASELINE configs[2]: 32 clips x 20 frames x 1024 tokens (256x256, stride 8), 8 heads; 16 sub-chunks per frame")
+
+    def long_clip():
+        W = WORKLOADS["long_clip"]
+        B, H, K, V, C = W["clips"], W["heads"], W["d_k"], W["d_v"], W["frame_tokens"]
+        T = W["frames"] * C
+        q2, k2, v2, g2, b2, s2 = make_device_inputs(B, T, H, K, V, 3333, dev)
+        o2 = torch.empty(B, T, H, V, dtype=torch.bfloat16, device=dev)
+        sA = torch.empty(B, H, K, V, dtype=torch.float32, device=dev)
+        sB = torch.empty_like(sA)
+        cut = (W["frames"] // 2) * C
+
+        def fn():      # two chained calls: frames 0-127, then 128-255 from the first call's final state
+            gdkvm_b200.gdr_lkva_out(q2[:, :cut], k2[:, :cut], v2[:, :cut], g2[:, :cut], b2[:, :cut], o2[:, :cut], sA, None, s2, C, 0)
+            gdkvm_b200.gdr_lkva_out(q2[:, cut:], k2[:, cut:], v2[:, cut:], g2[:, cut:], b2[:, cut:], o2[:, cut:], sB, None, sA, C, 0)
+        ms, steps, win = time_for(fn, args.extra_seconds)
+        ab = 2 * algorithmic_bytes(B, T // 2, H, K, V)       # the carried state is written and read once more
+        return extra_line(B, T, H, K, V, W["frames"], ms, steps, win, sampler,
+                          "BASELINE configs[3], one GPU's share: 64 clips x 256 frames x 49 tokens, 8 heads, TWO chained calls per step "
+                          "(state carried through final_state -> initial_state)", ab)
+
+    def varlen():
+        B, H, K, V, C = W1["clips"], W1["heads"], W1["d_k"], W1["d_v"], W1["frame_tokens"]
+        T = W1["frames"] * C
+        gen = torch.Generator().manual_seed(4321)
+        w = 1.0 + 0.5 * (2.0 * torch.rand(B, generator=gen) - 1.0)
+        fr = torch.clamp((w / w.sum() * B * W1["frames"]).round().long(), min=1)
+        fr[-1] += B * W1["frames"] - int(fr.sum())
+        cu = torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(fr * C, 0)]).to(dev)
+        pk = lambda t: t.reshape(1, B * T, *t.shape[2:])
+        qp, kp, vp, gp, bp = pk(q), pk(k), pk(v), pk(g), pk(beta)
+        o2 = torch.empty(1, B * T, H, V, dtype=torch.bfloat16, device=dev)
+        sT2 = torch.empty(B, H, K, V, dtype=torch.float32, device=dev)
+        fn = lambda: gdkvm_b200.gdr_lkva_varlen_out(qp, kp, vp, gp, bp, cu, o2, sT2, None, S0, 0)
+        ms, steps, win = time_for(fn, args.extra_seconds)
+        return extra_line(B, T, H, K, V, W1["frames"], ms, steps, win, sampler,
+                          f"configs[1]'s tokens packed (cu_seqlens on the device), clip lengths uniform in [0.5, 1.5] x 128 frames "
+                          f"(min {int(fr.min())}, max {int(fr.max())} frames)")
+
+    def fla():
+        t0 = time.time()
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--fla-child"], capture_output=True, text=True, timeout=420)
+        line = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+        if res.returncode != 0 or not line:
+            return {"unavailable": (res.stderr or res.stdout)[-300:]}
+        d = json.loads(line[-1])
+        win = d.pop("window")
+        d.update(unit=UNIT, speedup_of_this_kernel=d["ms_per_step"] / main_ms, clocks=sampler.window(*win) if sampler else None,
+                 note="flash-linear-attention 0.5.1 Triton chunk_gated_delta_rule (five launches, tcgen05 via Triton 3.6) on configs[1]'s "
+                      "inputs, same box, own process; informational comparator (SURVEY.md section 8d), never a dependency",
+                 wall_s=time.time() - t0)
+        return d
+
+    guarded("varlen_0.5", varlen)
+    guarded("camus", camus)
+    guarded("long_clip", long_clip)
+    if not args.no_fla:
+        guarded("fla_triton", fla)
+    return extra
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -186,12 +340,18 @@ def main():
     ap.add_argument("--clips", type=int, default=None, help="clips per GPU (default: the workload's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--compare-fla", action="store_true", help="also time fla's Triton path (informational)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra lines (other configs, comparators, sustained run)")
+    ap.add_argument("--no-fla", action="store_true", help="skip the fla Triton comparator (its Triton compile takes a minute)")
+    ap.add_argument("--sustained-seconds", type=float, default=2.5, help="length of the sustained run that follows the K-step burst")
+    ap.add_argument("--extra-seconds", type=float, default=0.8, help="length of each extra line's timed loop")
+    ap.add_argument("--fla-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(3, args.warmup)
     WORKLOAD.clear(); WORKLOAD.update(WORKLOADS[args.workload])
     if args.clips is None:
         args.clips = WORKLOAD["clips"]
+    if args.fla_child:
+        return fla_child()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -209,6 +369,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None        # one sampler for the whole run (sliced per region)
     from gdkvm_b200.host import bind_host_to_gpu
     host_cpus = None if args.no_numa else bind_host_to_gpu(local_rank)
     if world > 1:
@@ -249,10 +410,16 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    t_main0 = time.time()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = gdkvm_b200.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()          # cudaProfilerStart: `ncu --profile-from-start off` sees the timed region only
@@ -263,13 +430,34 @@ def main():
     barrier()
     torch.cuda.profiler.stop()
     launches = gdkvm_b200.launch_count() - launches0
-    ms_total = ev0.elapsed_time(ev1)
-    tmax = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_total = float(tmax.item())
-    ms_step = ms_total / args.steps
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1)) / args.steps
     value = world * B * W["frames"] / (ms_step * 1e-3)
+
+    # sustained: the same step back to back for a few seconds straight after the burst (a box slows by several per cent
+    # within seconds of load); the first and the last quarter are timed apart to show the drift
+    sustained = None
+    if not args.no_extras and args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(args.sustained_seconds * 1e3 / ms_step))
+        n_q = max(1, n_sus // 4)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        barrier()
+        t_s0 = time.time()
+        evs[0].record()
+        for i in range(n_sus):
+            if i == n_q:
+                evs[1].record()
+            if i == n_sus - n_q:
+                evs[2].record()
+            step()
+        evs[3].record()
+        barrier()
+        t_s1 = time.time()
+        sus_ms = max_over_ranks(evs[0].elapsed_time(evs[3])) / n_sus
+        first_q = max_over_ranks(evs[0].elapsed_time(evs[1])) / n_q
+        last_q = max_over_ranks(evs[2].elapsed_time(evs[3])) / n_q
+        sustained = {"seconds": evs[0].elapsed_time(evs[3]) * 1e-3, "steps": n_sus, "ms_per_step": sus_ms,
+                     "first_quarter_ms_per_step": first_q, "last_quarter_ms_per_step": last_q, "window": (t_s0, t_s1)}
+    t_main1 = time.time()
 
     # readout gather (the only collective; NOT on the hot path) timed separately
     gather_ms = None
@@ -277,16 +465,7 @@ def main():
         from gdkvm_b200.sharding import gather_readout
         for _ in range(2):
             gather_readout(o)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(3):
-            gather_readout(o)
-        e1.record()
-        barrier()
-        gm = torch.tensor([e0.elapsed_time(e1) / 3], device=dev)
-        dist.all_reduce(gm, op=dist.ReduceOp.MAX)
-        gather_ms = float(gm.item())
+        gather_ms = max_over_ranks(time_steps(lambda: gather_readout(o), 3, barrier))
 
     # end-to-end through the host-buffer API: pinned host tensors -> HBM -> kernel -> pinned host
     e2e = None
@@ -296,43 +475,60 @@ def main():
         pipe = HostPipeline(B, T, H, K, V, torch.bfloat16, torch.float32, clips_per_group=2, device=dev)
         ho, hsT = pipe.alloc_host_outputs()
         e2e_steps = max(1, min(args.steps, 5))
+        run = lambda compute=True: pipe.run(hq, hk, hv, hg, hb, hs, ho, hsT, None, C, args.flags, compute=compute)
         for _ in range(2):
-            pipe.run(hq, hk, hv, hg, hb, hs, ho, hsT, None, C, args.flags)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(e2e_steps):
-            pipe.run(hq, hk, hv, hg, hb, hs, ho, hsT, None, C, args.flags)
-        e1.record()
-        barrier()
-        em = torch.tensor([e0.elapsed_time(e1) / e2e_steps], device=dev)
-        if world > 1:
-            dist.all_reduce(em, op=dist.ReduceOp.MAX)
+            run()
+        t_e0 = time.time()
+        em = max_over_ranks(time_steps(run, e2e_steps, barrier))
+        t_e1 = time.time()
+        check = bool(torch.equal(ho.to(dev), o))
+        # the same bytes through the same pipeline with the kernel left out: the host <-> device copy floor of this box
+        run(False)
+        cm = max_over_ranks(time_steps(lambda: run(False), e2e_steps, barrier))
         h2d, d2h = pipe.bytes_per_call()
-        e2e = {"value": world * B * W["frames"] / (float(em.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": float(em.item()),
-               "steps": e2e_steps, "check": "readout matches device-resident run: %s" % bool(torch.equal(ho.to(dev), o)),
-               "host_cpus_bound": len(host_cpus) if host_cpus else None}
+        e2e = {"value": world * B * W["frames"] / (em * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": em,
+               "copy_only_ms": cm, "copy_only_GBps_per_gpu": (h2d + d2h) / (cm * 1e-3) / 1e9,
+               "kernel_ms_outside_the_copies": em - cm,
+               "steps": e2e_steps, "check": "readout matches device-resident run: %s" % check,
+               "host_cpus_bound": len(host_cpus) if host_cpus else None,
+               "clocks": sampler.window(t_e0, t_e1) if sampler is not None else None}
         del hq, hk, hv, hg, hb, hs, ho, hsT, pipe
-    clocks = sampler.stop() if sampler is not None else None
 
-    fla_cmp = None
-    if args.compare_fla and rank == 0:
+    # BASELINE configs[3] sharded over the ranks (N > 1): 512 long clips split by clip, two chained calls per step
+    sharded = None
+    if world > 1 and not args.no_extras and args.workload == "echonet_batch":
         try:
-            from fla.ops.gated_delta_rule import chunk_gated_delta_rule as fla_op
-            for _ in range(3):
-                fla_op(q, k, v, g, beta, initial_state=S0, output_final_state=True)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(5):
-                fla_op(q, k, v, g, beta, initial_state=S0, output_final_state=True)
-            e1.record()
-            torch.cuda.synchronize()
-            fla_cmp = {"ms_per_step": e0.elapsed_time(e1) / 5, "value": B * W["frames"] / (e0.elapsed_time(e1) / 5 * 1e-3),
-                       "note": "fla 0.5.1 Triton chunk_gated_delta_rule, same inputs; informational, never a dependency"}
+            WL = WORKLOADS["long_clip"]
+            Bl, Tl = 512 // world, WL["frames"] * WL["frame_tokens"]
+            base = make_device_inputs(min(Bl, 32), Tl, H, K, V, 3333 + rank, dev)
+            rep = (Bl + base[0].shape[0] - 1) // base[0].shape[0]
+            ql, kl, vl, gl, bl, sl = (t.repeat(rep, *([1] * (t.dim() - 1)))[:Bl].contiguous() for t in base)
+            ol = torch.empty(Bl, Tl, H, V, dtype=torch.bfloat16, device=dev)
+            sA = torch.empty(Bl, H, K, V, dtype=torch.float32, device=dev)
+            sB = torch.empty_like(sA)
+            cut = Tl // 2
+
+            def lstep():
+                gdkvm_b200.gdr_lkva_out(ql[:, :cut], kl[:, :cut], vl[:, :cut], gl[:, :cut], bl[:, :cut], ol[:, :cut], sA, None, sl, C, 0)
+                gdkvm_b200.gdr_lkva_out(ql[:, cut:], kl[:, cut:], vl[:, cut:], gl[:, cut:], bl[:, cut:], ol[:, cut:], sB, None, sA, C, 0)
+            for _ in range(2):
+                lstep()
+            lm = max_over_ranks(time_steps(lstep, 5, barrier))
+            ab = 2 * algorithmic_bytes(Bl, Tl // 2, H, K, V)
+            peak, _ = measured_peak_gbs()
+            sharded = {"ms_per_step": lm, "value": Bl * world * WL["frames"] / (lm * 1e-3), "unit": UNIT, "scaling": "strong",
+                       "clips_total": Bl * world, "clips_per_gpu": Bl, "frames": WL["frames"], "calls_per_step": 2,
+                       "roofline_frac_per_gpu": ab / (lm * 1e-3) / 1e9 / peak,
+                       "note": "BASELINE configs[3]: 512 clips x 256 frames x 49 tokens x 8 heads sharded by clip over the ranks, two "
+                               "chained calls (state carry), no collective; max over ranks"}
+            del ql, kl, vl, gl, bl, sl, ol, sA, sB, base
         except Exception as ex:  # noqa: BLE001
-            fla_cmp = {"unavailable": repr(ex)[:200]}
+            sharded = {"failed": repr(ex)[:300]}
+
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extras and args.workload == "echonet_batch" and varlen is None:
+        extra = run_extras(args, dev, sampler, (q, k, v, g, beta, S0), ms_step)
 
     if rank != 0:
         if world > 1:
@@ -363,6 +559,16 @@ def main():
             tpeak = 2250.0
         roofline["tensor_secondary"] = {"executed_TFLOPs": tf, "peak": tpeak, "frac": tf / tpeak,
                                         "algorithmic_TFLOPs": B * T * H * 6 * K * V / (ms_step * 1e-3) / 1e12}
+    if sustained is not None:
+        win = sustained.pop("window")
+        sustained["frac"] = abytes / (sustained["ms_per_step"] * 1e-3) / 1e9 / peak
+        sustained["last_quarter_frac"] = abytes / (sustained["last_quarter_ms_per_step"] * 1e-3) / 1e9 / peak
+        sustained["value"] = world * B * W["frames"] / (sustained["ms_per_step"] * 1e-3)
+        try:
+            sustained["peak_sustained_note"] = "fraction of the same burst copy peak as roofline.frac (MEASURED_PEAKS.json has no sustained HBM figure)"
+        except Exception:
+            pass
+        sustained["clocks"] = sampler.window(*win) if sampler is not None else None
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
@@ -385,6 +591,9 @@ def main():
                         "torch_fp32_value": 16 / t_t,
                         "torch_fp32_sample": f"oracle/gdr_ref.py recurrent, 1 clip x 16 frames x {H} heads in {t_t:.2f} s"}
 
+    # clocks of the contract's timed region: warm-up + K-step burst + the sustained run that follows it (one window; the
+    # burst alone is ~20 ms, shorter than a sampling interval)
+    clocks = sampler.window(t_main0, t_main1) if sampler is not None else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -400,10 +609,14 @@ def main():
                        "entry": "gdkvm_gdr_fwd_varlen (cu_seqlens on the device)"}} if varlen is not None else {}),
         "clocks": clocks,
     }
+    if sustained is not None:
+        line["sustained"] = sustained
     if gather_ms is not None:
         line["readout_gather_ms"] = gather_ms
-    if fla_cmp is not None:
-        line["fla_triton"] = fla_cmp
+    if sharded is not None:
+        line["extra"] = {"long_clip_sharded": sharded}
+    if extra is not None:
+        line["extra"] = extra
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

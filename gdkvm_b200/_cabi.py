@@ -19,7 +19,8 @@ def FLAG_SEGMENTS(n: int) -> int:
 
 EXPORTED_SYMBOLS = (
     "gdkvm_abi_version", "gdkvm_strerror", "gdkvm_last_cuda_error",
-    "gdkvm_gdr_fwd", "gdkvm_gdr_fwd_varlen", "gdkvm_gdr_plan", "gdkvm_gdr_plan_segments", "gdkvm_launch_count", "gdkvm_l2norm_fwd",
+    "gdkvm_gdr_fwd", "gdkvm_gdr_fwd_varlen", "gdkvm_gdr_plan", "gdkvm_gdr_plan_segments", "gdkvm_gdr_plan_reason",
+    "gdkvm_launch_count", "gdkvm_l2norm_fwd",
 )
 
 
@@ -66,6 +67,8 @@ def load() -> ctypes.CDLL:
             lib.gdkvm_gdr_plan.argtypes = [ctypes.POINTER(GdkvmGdrParams)]
             lib.gdkvm_gdr_plan_segments.restype = ctypes.c_int
             lib.gdkvm_gdr_plan_segments.argtypes = [ctypes.POINTER(GdkvmGdrParams), ctypes.c_int]
+            lib.gdkvm_gdr_plan_reason.restype = ctypes.c_char_p
+            lib.gdkvm_gdr_plan_reason.argtypes = [ctypes.POINTER(GdkvmGdrParams)]
             lib.gdkvm_launch_count.restype = ctypes.c_uint64
             lib.gdkvm_l2norm_fwd.restype = ctypes.c_int
             lib.gdkvm_l2norm_fwd.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,

@@ -100,6 +100,13 @@ int gdkvm_gdr_plan(const GdkvmGdrParams* params) {
     return gdkvm::pick(params);
 }
 
+const char* gdkvm_gdr_plan_reason(const GdkvmGdrParams* params) {
+    const int rc = gdkvm::validate(params);
+    if (rc != GDKVM_OK) return gdkvm_strerror(rc);
+    if (params->flags & GDKVM_FLAG_FORCE_RECURRENT) return "GDKVM_FLAG_FORCE_RECURRENT is set";
+    return gdkvm::chunked_unsupported_reason(*params);
+}
+
 int gdkvm_gdr_plan_segments(const GdkvmGdrParams* params, int sm_count) {
     const int rc = gdkvm::validate(params);
     if (rc != GDKVM_OK) return rc;
@@ -140,8 +147,17 @@ int gdkvm_gdr_fwd_varlen(const GdkvmGdrParams* params, const void* cu_seqlens, i
     int ce = gdkvm::device_is_sm100(&sm100);
     if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
     if (!sm100) return GDKVM_ERR_ARCH;
-    if (params->T == 0) return GDKVM_OK;
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (params->T == 0) {        // every clip is empty: the initial states pass through (zeros without one)
+        if (params->final_state != nullptr) {
+            const size_t bytes = (size_t)n_seqs * params->H * params->K * params->V * sizeof(float);
+            const cudaError_t e = params->initial_state != nullptr
+                ? cudaMemcpyAsync(params->final_state, params->initial_state, bytes, cudaMemcpyDeviceToDevice, stream)
+                : cudaMemsetAsync(params->final_state, 0, bytes, stream);
+            if (e != cudaSuccess) { gdkvm::tl_last_cuda_error = (int)e; return GDKVM_ERR_CUDA; }
+        }
+        return GDKVM_OK;
+    }
     ce = path == 1 ? gdkvm::launch_chunked_varlen(*params, cu_seqlens, cu_seqlens_bytes, n_seqs, stream)
                    : gdkvm::launch_recurrent_varlen(*params, cu_seqlens, cu_seqlens_bytes, n_seqs, stream);
     if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }

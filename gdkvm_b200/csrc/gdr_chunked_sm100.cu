@@ -622,7 +622,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                         uint32_t polls = 0;
                         while (ld_acquire_gpu(flag) < seg) {
                             __nanosleep(256);
-                            if (++polls > (1u << 25)) __trap();      // ~10 s: the predecessor died
+                            if (++polls > (1u << 28)) __trap();      // minutes (a debugger or a time-sliced GPU may stall a predecessor for seconds): it died
                         }
                     }
                     named_bar_sync(bar_id, 128);
@@ -971,32 +971,61 @@ int pick_segments(int chains, int nc, int sms) {
     return best;
 }
 
-bool device_has_mempools() {
-    int dev = 0, ok = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return false;
-    if (cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, dev) != cudaSuccess) { (void)cudaGetLastError(); return false; }
-    return ok != 0;
-}
+// Per-device facts and resources, created on first use under one mutex: SM count, memory-pool support, the dynamic
+// shared-memory opt-in of both kernel instantiations (cudaFuncSetAttribute is per device/context, so a process that
+// drives several GPUs needs it on each), and a library-PRIVATE stream-ordered memory pool for the hand-off scratch of
+// cut launches.  The pool keeps its blocks across synchronisations (release threshold = max) so the scratch is re-used
+// launch after launch; the process-wide default pool and its policy are never touched.
+struct DeviceCtx {
+    bool init = false;
+    int sms = 148;
+    bool mempools = false;
+    cudaMemPool_t pool = nullptr;      // nullptr: fall back to the default pool (unchanged policy)
+    cudaError_t attr_err = cudaErrorUnknown;
+};
 
-int device_sm_count() {
+DeviceCtx* device_ctx() {
     static std::mutex mu;
-    static int cached[64];
+    static DeviceCtx ctx[64];
+    static DeviceCtx overflow;         // device ordinals >= 64: re-initialised on every call (no caching)
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
     std::lock_guard<std::mutex> lk(mu);
-    if (cached[dev] == 0) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached[dev] = n;
-        // keep the stream-ordered pool's blocks across synchronisations (the hand-off scratch is re-used every launch)
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    DeviceCtx* c = (dev >= 0 && dev < 64) ? &ctx[dev] : &overflow;
+    if (c == &overflow) *c = DeviceCtx();
+    if (!c->init) {
+        int n = 0, ok = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) c->sms = n;
+        if (cudaDeviceGetAttribute(&ok, cudaDevAttrMemoryPoolsSupported, dev) == cudaSuccess) c->mempools = ok != 0;
+        if (c->mempools) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaMemPool_t pool = nullptr;
+            if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                c->pool = pool;
+            }
         }
         (void)cudaGetLastError();
+        c->init = true;
     }
-    return cached[dev];
+    if (c->attr_err != cudaSuccess) {      // retried until it has succeeded on THIS device
+        cudaError_t e = cudaFuncSetAttribute(gdr_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gdr_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) (void)cudaGetLastError();
+        c->attr_err = e;
+    }
+    return c;
+}
+
+// stream-ordered scratch of one launch: from the library's own pool when there is one
+cudaError_t scratch_alloc(void** ws, size_t bytes, const DeviceCtx* c, cudaStream_t stream) {
+    if (c != nullptr && c->pool != nullptr) return cudaMallocFromPoolAsync(ws, bytes, c->pool, stream);
+    return cudaMallocAsync(ws, bytes, stream);
 }
 
 }  // namespace
@@ -1023,18 +1052,25 @@ extern "C" int gdkvm_debug_phase_trace(long long* out, int n) {   // out[64][8]
 namespace gdkvm {
 #endif
 
-bool chunked_supports(const GdkvmGdrParams& p) {
-    if (p.io_dtype != GDKVM_BF16 || p.K != 64 || (p.V != 64 && p.V != 128 && p.V != 256) || p.T <= 0) return false;
+// Why the tcgen05 chunk kernel cannot take this problem ("" when it can).  Host arithmetic only.
+const char* chunked_unsupported_reason(const GdkvmGdrParams& p) {
+    if (p.io_dtype != GDKVM_BF16) return "q/k/v/o are fp32: the tcgen05 chunk kernel takes bf16 I/O (fp32 I/O runs the fp32 CUDA-core kernel)";
+    if (p.K != 64) return "d_k != 64: the tcgen05 chunk kernel is built for d_k = 64";
+    if (p.V != 64 && p.V != 128 && p.V != 256) return "d_v not in {64, 128, 256}";
+    if (p.T <= 0) return "no tokens";
     // TMA: 16-byte aligned bases and strides; the value/readout head stride must equal V so that
     // (head, 64-wide value block) folds into one tensor-map dimension.
     const void* ptrs[4] = {p.q, p.k, p.v, p.o};
-    for (const void* x : ptrs) if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0) return false;
+    for (const void* x : ptrs) if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0) return "q/k/v/o base pointers must be 16-byte aligned for TMA";
     for (int i = 0; i < 3; ++i)
-        if (!mult16(p.q_stride[i]) || !mult16(p.k_stride[i]) || !mult16(p.v_stride[i]) || !mult16(p.o_stride[i])) return false;
-    if (p.v_stride[2] != p.V || p.o_stride[2] != p.V) return false;
-    if (p.q_stride[1] <= 0 || p.k_stride[1] <= 0 || p.v_stride[1] <= 0 || p.o_stride[1] <= 0) return false;
-    return true;
+        if (!mult16(p.q_stride[i]) || !mult16(p.k_stride[i]) || !mult16(p.v_stride[i]) || !mult16(p.o_stride[i]))
+            return "q/k/v/o strides must be multiples of 16 bytes for TMA";
+    if (p.v_stride[2] != p.V || p.o_stride[2] != p.V) return "v/o head stride must equal d_v (heads contiguous inside a token)";
+    if (p.q_stride[1] <= 0 || p.k_stride[1] <= 0 || p.v_stride[1] <= 0 || p.o_stride[1] <= 0) return "token strides must be positive";
+    return "";
 }
+
+bool chunked_supports(const GdkvmGdrParams& p) { return chunked_unsupported_reason(p)[0] == '\0'; }
 
 int chunked_segments(const GdkvmGdrParams& p, int sms) {
     const bool flat = p.frame_tokens <= 0 || (p.flags & GDKVM_FLAG_FLAT_CHUNKS) ||
@@ -1048,20 +1084,6 @@ int chunked_segments(const GdkvmGdrParams& p, int sms) {
 }
 
 namespace {
-
-// dynamic shared memory opt-in of both kernel instantiations (per device: retried until it has succeeded)
-int ensure_smem_attr() {
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    auto set = [] {
-        cudaError_t e = cudaFuncSetAttribute(gdr_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gdr_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        return e;
-    };
-    std::call_once(once, [&] { attr_err = set(); });
-    if (attr_err != cudaSuccess) attr_err = set();      // another device may be current now
-    return (int)attr_err;
-}
 
 // Tensor maps of q, k (dk, token-in-frame, frame, head, clip) and v, o (64 values, token-in-frame, head x value block,
 // frame, clip): C tokens per frame, F frames; one 128-column value half per v / o box (each state warpgroup loads and
@@ -1160,8 +1182,9 @@ __global__ void __launch_bounds__(256) gdr_units_kernel(const IdxT* __restrict__
 }  // namespace
 
 int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
-    const int ae = ensure_smem_attr();
-    if (ae != 0) return ae;
+    const DeviceCtx* dc = device_ctx();
+    if (dc == nullptr) return (int)cudaErrorInvalidDevice;
+    if (dc->attr_err != cudaSuccess) return (int)dc->attr_err;
     // frame-aligned chunks when frames are whole 64-token chunks (or when asked for); otherwise tile the
     // flat token stream: identical results (token-causal recurrence), no zero-padded rows to process
     const bool flat = p.frame_tokens <= 0 || (p.flags & GDKVM_FLAG_FLAT_CHUNKS) ||
@@ -1180,14 +1203,14 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
     // under capture the scratch becomes allocation / free nodes of the graph (stream-ordered allocator); without memory-pool
     // support a captured launch stays uncut
     const bool capturing = cap != cudaStreamCaptureStatusNone;
-    int nseg = (capturing && !device_has_mempools()) ? 1 : chunked_segments(p, device_sm_count());
+    int nseg = (capturing && !dc->mempools) ? 1 : chunked_segments(p, dc->sms);
     int seg_chunks = (nc + nseg - 1) / nseg;
     float* xstate = nullptr;
     int* xsync = nullptr;
     void* ws = nullptr;
     if (nseg > 1) {
         const size_t state_bytes = (size_t)chains * 64 * V * sizeof(float), sync_bytes = ((size_t)chains * 2 + 1) * sizeof(int);
-        if (cudaMallocAsync(&ws, state_bytes + sync_bytes, stream) != cudaSuccess) {
+        if (scratch_alloc(&ws, state_bytes + sync_bytes, dc, stream) != cudaSuccess) {
             (void)cudaGetLastError();
             ws = nullptr; nseg = 1; seg_chunks = nc;                // same kernel, uncut chains
         } else {
@@ -1217,13 +1240,14 @@ int chunked_varlen_seg_chunks(const GdkvmGdrParams& p, int nseq, int sms) {
 // Packed variable-length sequences: q,k,v,o [1, T, H, *], sequence n = rows cu[n] .. cu[n+1]-1 (offsets on the device,
 // int32 or int64), states [nseq, H, K, V].
 int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream) {
-    const int ae = ensure_smem_attr();
-    if (ae != 0) return ae;
+    const DeviceCtx* dc = device_ctx();
+    if (dc == nullptr) return (int)cudaErrorInvalidDevice;
+    if (dc->attr_err != cudaSuccess) return (int)dc->attr_err;
     CUtensorMap mq, mk, mv, mo;
     const int me = make_maps(p, p.T, 1, &mq, &mk, &mv, &mo);
     if (me != 0) return me;
     const int H = p.H, V = p.V, chains = nseq * H;
-    const int seg_chunks = chunked_varlen_seg_chunks(p, nseq, device_sm_count());
+    const int seg_chunks = chunked_varlen_seg_chunks(p, nseq, dc->sms);
     // sum over sequences of round(chunks_n / seg_chunks)  <=  nseq + (sum of chunks) / seg_chunks,  sum of chunks <= T / 64 + nseq
     const int64_t max_entries64 = (int64_t)nseq + ((int64_t)p.T / 64 + nseq) / seg_chunks + 1;
     if (max_entries64 * H > 0x3fffffff) return (int)cudaErrorInvalidValue;
@@ -1232,7 +1256,7 @@ int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes,
     const size_t sync_bytes = (((size_t)chains * 2 + 1) * sizeof(int) + 15) & ~(size_t)15;
     const size_t tab_bytes = (size_t)kUnitInts * (1 + (size_t)max_entries) * sizeof(int);
     void* ws = nullptr;
-    cudaError_t e = cudaMallocAsync(&ws, state_bytes + sync_bytes + tab_bytes, stream);
+    cudaError_t e = scratch_alloc(&ws, state_bytes + sync_bytes + tab_bytes, dc, stream);
     if (e != cudaSuccess) return (int)e;
     float* xstate = reinterpret_cast<float*>(ws);
     int* xsync = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + state_bytes);

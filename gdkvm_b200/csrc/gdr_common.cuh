@@ -18,6 +18,8 @@ int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes,
 int launch_l2norm(const void* x, void* y, int64_t rows, int D, int64_t xs, int64_t ys, int dtype, float eps, cudaStream_t stream);
 // Host-side eligibility test of the chunked tcgen05 kernel (no GPU needed).
 bool chunked_supports(const GdkvmGdrParams& p);
+// ... and the reason when it is not eligible ("" when it is)
+const char* chunked_unsupported_reason(const GdkvmGdrParams& p);
 // Time segments per chain the chunked kernel would use on a device with `sms` SMs (host-side schedule simulation).
 int chunked_segments(const GdkvmGdrParams& p, int sms);
 

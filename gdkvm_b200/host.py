@@ -85,8 +85,10 @@ class HostPipeline:
 
     @torch.no_grad()
     def run(self, q, k, v, g, beta, initial_state: Optional[torch.Tensor], o_host, sT_host,
-            scale: Optional[float] = None, frame_tokens: int = 0, flags: int = 0) -> None:
-        """Enqueue the whole batch; returns after the last device->host copy has completed."""
+            scale: Optional[float] = None, frame_tokens: int = 0, flags: int = 0, compute: bool = True) -> None:
+        """Enqueue the whole batch; returns after the last device->host copy has completed.  ``compute=False`` skips
+        the kernel and moves the same bytes (the copy-only floor of this pipeline on this host: bench.py's
+        ``e2e.copy_only_ms``)."""
         B = self.geom[0]
         if (initial_state is not None) != self.with_s0:
             raise ValueError("initial_state presence must match with_initial_state")
@@ -109,8 +111,9 @@ class HostPipeline:
                 slot.h2d_done.record(self.s_h2d)
             with torch.cuda.stream(self.s_comp):
                 self.s_comp.wait_event(slot.h2d_done)
-                gdr_lkva_out(slot.q[:n], slot.k[:n], slot.v[:n], slot.g[:n], slot.beta[:n], slot.o[:n],
-                             slot.sT[:n], scale, slot.s0[:n] if self.with_s0 else None, frame_tokens, flags)
+                if compute:
+                    gdr_lkva_out(slot.q[:n], slot.k[:n], slot.v[:n], slot.g[:n], slot.beta[:n], slot.o[:n],
+                                 slot.sT[:n], scale, slot.s0[:n] if self.with_s0 else None, frame_tokens, flags)
                 slot.compute_done.record(self.s_comp)
             with torch.cuda.stream(self.s_d2h):
                 self.s_d2h.wait_event(slot.compute_done)

@@ -16,14 +16,16 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
+import warnings
 from typing import Optional, Tuple
 
 import torch
 
 from . import _cabi
 
-__all__ = ["gdr_lkva", "gdr_lkva_out", "gdr_lkva_varlen", "chunk_gated_delta_rule", "l2norm", "plan", "plan_segments",
-           "launch_count"]
+__all__ = ["gdr_lkva", "gdr_lkva_out", "gdr_lkva_varlen", "gdr_lkva_varlen_out", "check_inputs", "chunk_gated_delta_rule", "l2norm", "plan", "plan_reason",
+           "plan_segments", "launch_count"]
 
 _DT = {torch.float32: _cabi.GDKVM_F32, torch.bfloat16: _cabi.GDKVM_BF16}
 
@@ -54,7 +56,31 @@ def _make_params(q, k, v, g, beta, o, s0, sT, scale, frame_tokens, flags) -> _ca
     return p
 
 
+def _same_device(q, **others):
+    """Every tensor of a call must live on q's CUDA device: the op hands raw pointers to the kernel / to TMA, and a
+    host pointer or another GPU's pointer there is an illegal-address fault (sticky: it kills the CUDA context)."""
+    for name, t in others.items():
+        if t is not None and t.device != q.device:
+            raise ValueError(f"{name} is on {t.device} but q is on {q.device}: all tensors of one call must share one device")
+
+
+_warned_fallback = set()
+_CHECK_INPUTS = os.environ.get("GDKVM_CHECK_INPUTS", "0") not in ("", "0")
+
+
+def _warn_fallback(lib, p, what):
+    """Loud, once per reason: an un-forced call that the tcgen05 kernel cannot take runs the fp32 CUDA-core kernel."""
+    if p.flags & (_cabi.FLAG_FORCE_RECURRENT | _cabi.FLAG_FORCE_CHUNKED) or p.T == 0:
+        return
+    reason = lib.gdkvm_gdr_plan_reason(ctypes.byref(p)).decode()
+    if reason and reason not in _warned_fallback:
+        _warned_fallback.add(reason)
+        warnings.warn(f"{what}: running the token-recurrent fp32 CUDA-core kernel (several times slower than the tcgen05 "
+                      f"chunk kernel) because {reason}", RuntimeWarning, stacklevel=3)
+
+
 def _check(q, k, v, g, beta, initial_state):
+    _same_device(q, k=k, v=v, g=g, beta=beta, initial_state=initial_state)
     if q.dim() != 4 or k.shape != q.shape or v.dim() != 4 or v.shape[:3] != q.shape[:3]:
         raise ValueError("expected q,k [B,T,H,K] and v [B,T,H,V]")
     if g.shape != q.shape[:3] or beta.shape != q.shape[:3]:
@@ -91,6 +117,7 @@ def gdr_lkva_out(q, k, v, g, beta, o, final_state=None, scale=None, initial_stat
     if not q.is_cuda:
         raise RuntimeError("gdkvm_b200 runs on a B200 only; there is no CPU implementation of gdr_lkva")
     lib = _cabi.load()
+    _same_device(q, o=o, final_state=final_state)
     B, T, H, K = k.shape
     V = v.shape[-1]
     if o.shape != (B, T, H, V) or o.dtype != q.dtype or o.stride(-1) != 1:
@@ -103,6 +130,9 @@ def gdr_lkva_out(q, k, v, g, beta, o, final_state=None, scale=None, initial_stat
     if scale is None:
         scale = 1.0 / math.sqrt(K)
     p = _make_params(q, k, v, g, beta, o, initial_state, final_state, scale, frame_tokens, flags)
+    if _CHECK_INPUTS:
+        check_inputs(k, beta)
+    _warn_fallback(lib, p, "gdkvm_b200.gdr_lkva")
     with torch.cuda.device(q.device):
         rc = lib.gdkvm_gdr_fwd(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0:
@@ -141,35 +171,50 @@ torch.library.define(
 )
 
 
-@torch.library.impl("gdkvm::gdr_lkva_varlen", "CUDA")
-def _gdr_lkva_varlen_cuda(q, k, v, g, beta, cu_seqlens, scale=None, initial_state=None, output_final_state=True, flags=0):
+def gdr_lkva_varlen_out(q, k, v, g, beta, cu_seqlens, o, final_state=None, scale=None, initial_state=None, flags=0) -> None:
+    """The packed variable-length call into caller-owned ``o`` [1,T,H,V] (and ``final_state`` [N,H,K,V]): the C-ABI call
+    with torch tensors as buffer owners.  Rows of ``o`` that belong to no clip (before ``cu_seqlens[0]``, from
+    ``cu_seqlens[-1]`` on) are not written."""
     _check(q, k, v, g, beta, None)
+    if not q.is_cuda:
+        raise RuntimeError("gdkvm_b200 runs on a B200 only; there is no CPU implementation of gdr_lkva_varlen")
+    _same_device(q, cu_seqlens=cu_seqlens, initial_state=initial_state, o=o, final_state=final_state)
     B, T, H, K = k.shape
     V = v.shape[-1]
     if B != 1:
         raise ValueError("packed variable-length clips: q,k,v must be [1, total_tokens, H, *]")
     if cu_seqlens.dim() != 1 or cu_seqlens.numel() < 2 or cu_seqlens.dtype not in (torch.int32, torch.int64):
         raise ValueError("cu_seqlens must be a 1-D int32/int64 tensor of n_seqs + 1 offsets")
-    if not cu_seqlens.is_cuda:
-        raise ValueError("cu_seqlens must live on the device (it is never read on the host)")
     N = cu_seqlens.numel() - 1
     cu = cu_seqlens.contiguous()
-    if initial_state is not None:
-        if initial_state.shape != (N, H, K, V) or initial_state.dtype != torch.float32:
-            raise ValueError("initial_state must be fp32 [n_seqs,H,K,V]")
-        initial_state = initial_state.contiguous()
-    o = torch.empty((1, T, H, V), dtype=q.dtype, device=q.device)
-    sT = torch.empty((N, H, K, V) if output_final_state else (0,), dtype=torch.float32, device=q.device)
+    if o.shape != (1, T, H, V) or o.dtype != q.dtype or o.stride(-1) != 1:
+        raise ValueError("o must be [1,T,H,V] in q.dtype with a contiguous last dimension")
+    for name, st in (("initial_state", initial_state), ("final_state", final_state)):
+        if st is not None and (st.shape != (N, H, K, V) or st.dtype != torch.float32 or not st.is_contiguous()):
+            raise ValueError(f"{name} must be contiguous fp32 [n_seqs,H,K,V]")
     if scale is None:
         scale = 1.0 / math.sqrt(K)
-    p = _make_params(q, k, v, g, beta, o, initial_state, sT if output_final_state else None, scale, 0, flags)
+    p = _make_params(q, k, v, g, beta, o, initial_state, final_state, scale, 0, flags)
     lib = _cabi.load()
+    _warn_fallback(lib, p, "gdkvm_b200.gdr_lkva_varlen")
     with torch.cuda.device(q.device):
         rc = lib.gdkvm_gdr_fwd_varlen(ctypes.byref(p), ctypes.c_void_p(cu.data_ptr()), cu.element_size(), N,
                                       ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0:
         extra = f" (cudaError {lib.gdkvm_last_cuda_error()})" if rc == -7 else ""
         raise RuntimeError(f"gdkvm_gdr_fwd_varlen: {_cabi.strerror(rc)}{extra}")
+
+
+@torch.library.impl("gdkvm::gdr_lkva_varlen", "CUDA")
+def _gdr_lkva_varlen_cuda(q, k, v, g, beta, cu_seqlens, scale=None, initial_state=None, output_final_state=True, flags=0):
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    N = cu_seqlens.numel() - 1
+    if initial_state is not None:
+        initial_state = initial_state.contiguous()
+    o = torch.empty((1, T, H, V), dtype=q.dtype, device=q.device)
+    sT = torch.empty((N, H, K, V) if output_final_state else (0,), dtype=torch.float32, device=q.device)
+    gdr_lkva_varlen_out(q, k, v, g, beta, cu_seqlens, o, sT if output_final_state else None, scale, initial_state, flags)
     return o, sT
 
 
@@ -205,6 +250,24 @@ def _l2norm_cuda(x, eps=1e-6):
 @torch.library.register_fake("gdkvm::l2norm")
 def _l2norm_fake(x, eps=1e-6):
     return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+
+def _l2norm_setup(ctx, inputs, output):
+    x, eps = inputs
+    ctx.save_for_backward(x)
+    ctx.eps = eps
+
+
+def _l2norm_backward(ctx, dy):
+    # y = x r, r = rsqrt(sum x^2 + eps):  dx = r (dy - y (y . dy))   (elementwise torch ops; not a hot path)
+    (x,) = ctx.saved_tensors
+    xf, dyf = x.float(), dy.float()
+    r = torch.rsqrt(xf.square().sum(-1, keepdim=True) + ctx.eps)
+    y = xf * r
+    return (r * (dyf - y * (y * dyf).sum(-1, keepdim=True))).to(x.dtype), None
+
+
+torch.library.register_autograd("gdkvm::l2norm", _l2norm_backward, setup_context=_l2norm_setup)
 
 
 def l2norm(x: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
@@ -258,6 +321,20 @@ def chunk_gated_delta_rule(q, k, v, g, beta, scale=None, initial_state=None, out
                     kwargs.get("frame_tokens", 0), kwargs.get("flags", 0))
 
 
+def check_inputs(k: torch.Tensor, beta: torch.Tensor) -> float:
+    """Debugging aid for the one numerical precondition of the op: ``beta_i |k_i|^2 <= 2`` for every token.  Beyond it the
+    delta rule itself is unstable (the factor ``I - beta k k^T`` has an eigenvalue below -1, so the state grows
+    geometrically in exact arithmetic too), and the tcgen05 kernel's fp16 triangular solve overflows where the fp32
+    recurrence would merely explode.  L2-normalised keys (``l2norm`` / ``use_qk_l2norm_in_kernel``) with beta in (0, 1)
+    are always inside.  Synchronises; returns the maximum of ``beta |k|^2`` and raises ``ValueError`` above 2.
+    Called on every op call when the environment variable ``GDKVM_CHECK_INPUTS=1`` is set."""
+    m = float((beta.float() * k.float().square().sum(-1)).max()) if k.numel() else 0.0
+    if not m <= 2.0:
+        raise ValueError(f"gdkvm_b200: max beta |k|^2 = {m:.3g} > 2: the gated delta rule is unstable for these inputs "
+                         "(normalise k, or scale beta by 1/|k|^2)")
+    return m
+
+
 def plan(q, k, v, g, beta, *, frame_tokens: int = 0, flags: int = 0) -> int:
     """Which kernel the library would pick (0 recurrent, 1 tcgen05 chunked); needs no GPU."""
     _check(q, k, v, g, beta, None)
@@ -267,6 +344,13 @@ def plan(q, k, v, g, beta, *, frame_tokens: int = 0, flags: int = 0) -> int:
     if rc < 0:
         raise RuntimeError(f"gdkvm_gdr_plan: {_cabi.strerror(rc)}")
     return rc
+
+
+def plan_reason(q, k, v, g, beta, *, frame_tokens: int = 0, flags: int = 0) -> str:
+    """Why the library would NOT take the tcgen05 chunk kernel for these tensors ("" when it would); needs no GPU."""
+    _check(q, k, v, g, beta, None)
+    p = _make_params(q, k, v, g, beta, v, None, None, 1.0, frame_tokens, flags)
+    return _cabi.load().gdkvm_gdr_plan_reason(ctypes.byref(p)).decode()
 
 
 def plan_segments(q, k, v, g, beta, *, frame_tokens: int = 0, flags: int = 0, sm_count: int = 0) -> int:

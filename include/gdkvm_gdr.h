@@ -11,8 +11,11 @@
  * (fla/ops/gated_delta_rule/chunk.py:365-377), the op the upstream model most plausibly calls.
  *
  * Conventions: plain C, no torch/C++ types, caller-owned buffers, errors as negative ints (no
- * exceptions cross the ABI), asynchronous on the caller's CUDA stream, CUDA-graph capturable
- * (no host sync, no allocation after the first call on a device), re-entrant.
+ * exceptions cross the ABI), asynchronous on the caller's CUDA stream, CUDA-graph capturable, re-entrant.
+ * No host synchronisation and no user-visible allocation, ever.  Internal memory: a launch whose chains are cut into
+ * time segments (and every packed variable-length launch) takes a per-launch scratch with a stream-ordered
+ * allocation from a memory pool the LIBRARY owns (created on first use per device; the process-wide default pool and
+ * its release policy are never touched); under stream capture that scratch becomes alloc / free nodes of the graph.
  */
 #ifndef GDKVM_GDR_H_
 #define GDKVM_GDR_H_
@@ -119,8 +122,9 @@ int gdkvm_gdr_fwd(const GdkvmGdrParams* params, void* cuda_stream);
  *   replaces: the `cu_seqlens` argument of fla's chunk_gated_delta_rule (fla/ops/gated_delta_rule/chunk.py:375);
  *   SURVEY.md section 8f rank 4.
  * params->B must be 1 and params->T the total number of tokens: q,k [1,T,H,K], v,o [1,T,H,V], g,beta [1,T,H].  Clip n
- * is rows cu_seqlens[n] .. cu_seqlens[n+1]-1 (n = 0..n_seqs-1; cu_seqlens[0] = 0, cu_seqlens[n_seqs] = T,
- * non-decreasing), an array of n_seqs+1 offsets in DEVICE memory of cu_seqlens_bytes (4 or 8) bytes each -- the
+ * is rows cu_seqlens[n] .. cu_seqlens[n+1]-1 (n = 0..n_seqs-1; non-decreasing, 0 <= cu_seqlens[0], cu_seqlens[n_seqs]
+ * <= T; rows of o outside every clip are never written, rows of q/k/v there may be read and must hold finite
+ * numbers), an array of n_seqs+1 offsets in DEVICE memory of cu_seqlens_bytes (4 or 8) bytes each -- the
  * library never reads it on the host, so the call stays asynchronous.  initial_state / final_state are
  * [n_seqs, H, K, V]; a clip without tokens passes its initial state through.  frame_tokens is ignored (flat 64-token
  * tiling; token-causal semantics make that exactly equivalent).  Uses a stream-ordered per-launch workspace
@@ -137,9 +141,16 @@ int gdkvm_gdr_fwd_varlen(const GdkvmGdrParams* params, const void* cu_seqlens, i
 int gdkvm_gdr_plan(const GdkvmGdrParams* params);
 
 /*
+ * Why gdkvm_gdr_fwd would NOT take the tcgen05 chunk kernel for `params` (static string; "" when it would): a call that
+ * drops to the fp32 CUDA-core kernel is several times slower, and this is how a caller finds out why.  Needs no GPU.
+ */
+const char* gdkvm_gdr_plan_reason(const GdkvmGdrParams* params);
+
+/*
  * Time segments per chain gdkvm_gdr_fwd would cut the problem into on a device with `sm_count` SMs (<= 0: 148, a B200):
  * 1 = one work unit per (clip, head) chain; n > 1 = n units per chain, scheduled in order, so that the last wave of
- * units over the SMs is not ragged (GDKVM_FLAG_SEGMENTS overrides; launches under stream capture are never cut).
+ * units over the SMs is not ragged (GDKVM_FLAG_SEGMENTS overrides; launches under stream capture are cut the same
+ * way when the device supports memory pools -- the scratch lives in the graph -- and stay uncut otherwise).
  * Pure host arithmetic, needs no GPU.  Returns 1 for the recurrent path, negative = GdkvmStatus.
  */
 int gdkvm_gdr_plan_segments(const GdkvmGdrParams* params, int sm_count);

@@ -222,3 +222,42 @@ def max_rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     a = a.detach().to("cpu", torch.float32)
     b = b.detach().to("cpu", torch.float32)
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def rms_rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    """Root-mean-square error relative to the reference's RMS: ||a-b||_2 / ||b||_2 per tensor.  Unlike ``max_rel_err``
+    it is not set by one outlier element, and unlike a per-element relative error it is defined where b crosses zero."""
+    a = a.detach().to("cpu", torch.float64)
+    b = b.detach().to("cpu", torch.float64)
+    return float((a - b).square().mean().sqrt() / b.square().mean().sqrt().clamp_min(1e-30))
+
+
+def per_clip_errors(o, o_ref, sT=None, s_ref=None):
+    """[(clip, head) -> max-rel of the readout, rms-rel of the readout, max-rel of the final state] for every chain of a
+    batched call (o [B,T,H,V], states [B,H,K,V]): a chain with small-magnitude outputs must not hide behind the batch's
+    largest element, which is what a whole-tensor ``max_rel_err`` allows."""
+    o = o.detach().to("cpu", torch.float32)
+    o_ref = o_ref.detach().to("cpu", torch.float32)
+    B, T, H, V = o_ref.shape
+    d = (o - o_ref)
+    mo = d.abs().amax(dim=(1, 3)) / o_ref.abs().amax(dim=(1, 3)).clamp_min(1e-30)                         # [B,H]
+    ro = d.double().square().mean(dim=(1, 3)).sqrt() / o_ref.double().square().mean(dim=(1, 3)).sqrt().clamp_min(1e-30)
+    ms = None
+    if sT is not None:
+        sT = sT.detach().to("cpu", torch.float32)
+        s_ref = s_ref.detach().to("cpu", torch.float32)
+        ms = (sT - s_ref).abs().amax(dim=(2, 3)) / s_ref.abs().amax(dim=(2, 3)).clamp_min(1e-30)
+    return mo, ro.float(), ms
+
+
+def per_frame_max_rel(o, o_ref, frame_tokens: int):
+    """Error growth along a clip: for every frame f, max over (clip, head) of max|a-b| / max|b| taken over that frame's
+    rows of that chain only.  Returns a 1-D tensor of length T / frame_tokens."""
+    o = o.detach().to("cpu", torch.float32)
+    o_ref = o_ref.detach().to("cpu", torch.float32)
+    B, T, H, V = o_ref.shape
+    F = T // frame_tokens
+    a = o[:, :F * frame_tokens].reshape(B, F, frame_tokens, H, V)
+    b = o_ref[:, :F * frame_tokens].reshape(B, F, frame_tokens, H, V)
+    e = (a - b).abs().amax(dim=(2, 4)) / b.abs().amax(dim=(2, 4)).clamp_min(1e-30)                         # [B,F,H]
+    return e.amax(dim=(0, 2))

@@ -11,13 +11,15 @@ import numpy as np
 import pytest
 import torch
 
-from oracle.gdr_ref import gdr_recurrent_ref, gdr_recurrent_varlen_ref, make_inputs, max_rel_err
+import golden_util
+from oracle.gdr_ref import (gdr_recurrent_ref, gdr_recurrent_varlen_ref, make_inputs, max_rel_err, per_clip_errors, per_frame_max_rel,
+                            rms_rel_err)
 
 pytestmark = pytest.mark.gpu
 
 TOL = {torch.float32: 1e-3, torch.bfloat16: 2e-2}
 RECURRENT, CHUNKED, FLAT, FRAME = 0x1, 0x2, 0x4, 0x8
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = golden_util.FP32
 
 
 def SEG(n):
@@ -40,6 +42,15 @@ def _run(op, q, k, v, g, beta, S0, **kw):
     o, sT = op.gdr_lkva(qd, kd, vd, gd, bd, kw.pop("scale", None), sd, True, **kw)
     torch.cuda.synchronize()
     return o.float().cpu(), sT.cpu()
+
+
+def _assert_per_chain(o, o_ref, sT, s_ref, tol, what=""):
+    """The tolerance per (clip, head) chain -- max-rel of the readout and of the final state over that chain's own
+    elements, so a chain with small outputs cannot hide behind the batch maximum -- and the RMS error well inside it."""
+    mo, ro, ms = per_clip_errors(o, o_ref, sT, s_ref)
+    assert float(mo.max()) <= tol, (what, "readout max-rel per chain", mo)
+    assert ms is None or float(ms.max()) <= tol, (what, "final state max-rel per chain", ms)
+    assert float(ro.max()) <= tol / 2, (what, "readout rms-rel per chain", ro)
 
 
 def _paths(op, q, k, v, g, beta, C):
@@ -71,6 +82,7 @@ def test_parity_vs_oracle(op, shape, dtype):
         o, sT = _run(op, q, k, v, g, beta, S0, frame_tokens=C, **kw)
         eo, es = max_rel_err(o, o_ref), max_rel_err(sT, s_ref)
         assert eo <= TOL[dtype] and es <= TOL[dtype], (name, eo, es)
+        _assert_per_chain(o, o_ref, sT, s_ref, TOL[dtype], name)
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -81,6 +93,20 @@ def test_golden_fixtures(op, path):
     for name, kw in _paths(op, t["q"], t["k"], t["v"], t["g"], t["beta"], C):
         o, sT = _run(op, t["q"], t["k"], t["v"], t["g"], t["beta"], t["s0"], frame_tokens=C, **kw)
         assert max_rel_err(o, t["o"]) <= 1e-3 and max_rel_err(sT, t["sT"]) <= 1e-3, name
+
+
+@pytest.mark.parametrize("path", golden_util.BF16, ids=golden_util.ids(golden_util.BF16))
+def test_bf16_golden_through_the_chunk_kernel(op, path):
+    """The tcgen05 kernel, FORCED, against the independent goldens (fla-naive on the same bf16-rounded q, k, v; a 256-frame
+    clip = 196 chunks and 1024-token frames included): frame-aligned, flat and time-segmented tiling, per chain, RMS too."""
+    q, k, v, g, beta, S0, rows, o_rows, sT_ref, C = golden_util.load_bf16(path)
+    assert op.plan(q.cuda(), k.cuda(), v.cuda(), g.cuda(), beta.cuda(), frame_tokens=C, flags=CHUNKED) == 1
+    for fl in (CHUNKED, CHUNKED | FLAT, CHUNKED | FRAME, CHUNKED | SEG(3)):
+        o, sT = _run(op, q, k, v, g, beta, S0, frame_tokens=C, flags=fl)
+        eo, es = max_rel_err(o[:, rows], o_rows), max_rel_err(sT, sT_ref)
+        assert eo <= 2e-2 and es <= 2e-2, (fl, eo, es)
+        _assert_per_chain(o[:, rows], o_rows, sT, sT_ref, 2e-2, fl)
+        assert rms_rel_err(o[:, rows], o_rows) <= 1e-2 and rms_rel_err(sT, sT_ref) <= 1e-2
 
 
 def test_recurrent_kernel_is_fp32_exact(op):
@@ -481,16 +507,105 @@ def test_varlen_equals_batched_call_bit_for_bit(op):
 
 
 def test_varlen_rows_outside_every_clip_are_untouched(op):
-    """The last chunk of a clip is stored row by row: the readout rows of the NEXT clip must come from that clip only,
-    whatever order the work units finish in (run twice with a poisoned output buffer in between)."""
+    """Caller-owned, NaN-poisoned readout buffer with rows that belong to no clip (a gap before the first clip and behind
+    the last one): the packed call -- TMA stores for whole chunks, row-wise stores for a clip's last chunk -- must write
+    every row of every clip and not one bit elsewhere, on the tcgen05 and on the recurrent path."""
     lens = [70, 3, 129, 64, 1]
-    q, k, v, g, beta, S0, cu = _packed(lens, 2, 256, 53)
+    lead, trail = 5, 9
+    T = lead + sum(lens) + trail
+    q, k, v, g, beta, _ = make_inputs(1, T, 2, 64, 256, seed=53, dtype=torch.bfloat16)
+    S0 = 0.1 * torch.randn(len(lens), 2, 64, 256, generator=torch.Generator().manual_seed(54))
+    cu = torch.tensor([lead] + [lead + int(x) for x in np.cumsum(lens)], dtype=torch.int64)
     qd, kd, vd, gd, bd, sd = _dev(q, k, v, g, beta, S0)
-    cud = cu.cuda()
-    o1, s1 = op.gdr_lkva_varlen(qd, kd, vd, gd, bd, cud, None, sd, True, CHUNKED)
-    for _ in range(3):
-        o2, s2 = op.gdr_lkva_varlen(qd, kd, vd, gd, bd, cud, None, sd, True, CHUNKED)
-        assert torch.equal(o1, o2) and torch.equal(s1, s2)
+    for flags in (CHUNKED, CHUNKED | SEG(2), RECURRENT):
+        o = torch.full((1, T, 2, 256), float("nan"), dtype=torch.bfloat16, device="cuda")
+        sT = torch.full((len(lens), 2, 64, 256), float("nan"), device="cuda")
+        op.gdr_lkva_varlen_out(qd, kd, vd, gd, bd, cu.cuda(), o, sT, None, sd, flags)
+        torch.cuda.synchronize()
+        assert bool(torch.isnan(o[:, :lead]).all()) and bool(torch.isnan(o[:, T - trail:]).all()), flags
+        assert not bool(torch.isnan(o[:, lead:T - trail]).any()) and not bool(torch.isnan(sT).any()), flags
+        for n in range(len(lens)):          # every clip alone (its own launch) gives the same rows
+            a, b = int(cu[n]), int(cu[n + 1])
+            o_n, s_n = gdr_recurrent_ref(q[:, a:b], k[:, a:b], v[:, a:b], g[:, a:b], beta[:, a:b], None, S0[n:n + 1])
+            assert max_rel_err(o[:, a:b], o_n) <= 2e-2 and max_rel_err(sT[n:n + 1], s_n) <= 2e-2, (flags, n)
+
+
+def test_varlen_all_clips_empty_pass_their_state_through(op):
+    q, k, v, g, beta, _ = _dev(*make_inputs(1, 0, 2, 64, 256, seed=55, dtype=torch.bfloat16))
+    S0 = torch.randn(3, 2, 64, 256, device="cuda")
+    cu = torch.zeros(4, dtype=torch.int32, device="cuda")
+    o, sT = op.gdr_lkva_varlen(q, k, v, g, beta, cu, None, S0, True, 0)
+    assert o.shape == (1, 0, 2, 256) and torch.equal(sT, S0)
+    _, sT0 = op.gdr_lkva_varlen(q, k, v, g, beta, cu, None, None, True, 0)
+    assert torch.equal(sT0, torch.zeros_like(S0))
+
+
+def test_mixed_devices_are_rejected_before_the_launch(op):
+    """A host tensor (or another GPU's) among the arguments would hand the kernel a pointer it cannot dereference."""
+    q, k, v, g, beta, S0 = make_inputs(1, 64, 1, 64, 64, seed=2, dtype=torch.bfloat16)
+    qd, kd, vd, gd, bd, sd = _dev(q, k, v, g, beta, S0)
+    for bad in ("g", "beta", "k", "initial_state"):
+        args = dict(q=qd, k=kd, v=vd, g=gd, beta=bd, initial_state=sd)
+        args[bad] = dict(q=q, k=k, v=v, g=g, beta=beta, initial_state=S0)[bad]
+        with pytest.raises((ValueError, RuntimeError)):
+            op.gdr_lkva(args["q"], args["k"], args["v"], args["g"], args["beta"], None, args["initial_state"])
+    with pytest.raises(ValueError):
+        op.gdr_lkva_out(qd, kd, vd, gd, bd, torch.empty(1, 64, 1, 64, dtype=torch.bfloat16), None)
+    cu = torch.tensor([0, 64], dtype=torch.int32)
+    with pytest.raises((ValueError, RuntimeError)):
+        op.gdr_lkva_varlen(qd, kd, vd, gd, bd, cu)                   # cu_seqlens on the host
+    torch.cuda.synchronize()                                        # the context is still alive
+    o, _ = op.gdr_lkva(qd, kd, vd, gd, bd, None, sd)
+    assert bool(torch.isfinite(o.float()).all())
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_one_process(op):
+    """The tcgen05 kernel's shared-memory opt-in is per device: cuda:1 after cuda:0 in the same process."""
+    q, k, v, g, beta, S0 = make_inputs(2, 5 * 64, 2, 64, 256, seed=91, dtype=torch.bfloat16)
+    outs = []
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        t = [x.to(dev) for x in (q, k, v, g, beta, S0)]
+        o, sT = op.gdr_lkva(*t[:5], None, t[5], True, 0, CHUNKED | SEG(2))
+        torch.cuda.synchronize(dev)
+        outs.append((o.cpu(), sT.cpu()))
+    assert all(torch.equal(outs[0][0], x[0]) and torch.equal(outs[0][1], x[1]) for x in outs[1:])
+
+
+def test_unforced_fallback_warns_once_with_the_reason(op):
+    q, k, v, g, beta, S0 = _dev(*make_inputs(1, 40, 1, 64, 64, seed=3))         # fp32 I/O: not the tcgen05 kernel
+    assert "fp32" in op.plan_reason(q, k, v, g, beta) and op.plan(q, k, v, g, beta) == 0
+    assert op.plan_reason(q.bfloat16(), k.bfloat16(), v.bfloat16(), g, beta) == ""
+    from gdkvm_b200 import ops
+    ops._warned_fallback.clear()
+    with pytest.warns(RuntimeWarning, match="fp32"):
+        op.gdr_lkva(q, k, v, g, beta, None, S0)
+    import warnings as w
+    with w.catch_warnings():
+        w.simplefilter("error")
+        op.gdr_lkva(q, k, v, g, beta, None, S0)                                   # second call: silent
+        op.gdr_lkva(q, k, v, g, beta, None, S0, True, 0, RECURRENT)              # forced: never warns
+
+
+@pytest.mark.parametrize("norm", [1.0, 1.25, 1.5, 2.0, 4.0])
+def test_key_norm_envelope_of_the_fp16_solve(op, norm):
+    """Un-normalised, strongly correlated keys (one base key per 64-token frame + 0.3 noise, |k| = norm): the intra-chunk
+    system (I + A), A_ij = beta_i k_i.k_j, is solved in fp16 on the tcgen05 path.  Inside the stability envelope of the
+    delta rule itself -- beta |k|^2 <= 2, here beta is drawn in (0, 1.8 / norm^2) -- the chunk kernel must hold the bf16
+    tolerance against the fp32 oracle; check_inputs() is the loud check of that precondition."""
+    C = 64
+    q, k, v, g, beta, S0 = make_inputs(2, 6 * C, 2, 64, 256, seed=81, frame_tokens=C, correlated=True, dtype=torch.float32)
+    k = (k * norm).bfloat16()
+    q, v = q.bfloat16(), v.bfloat16()
+    beta = beta * min(1.0, 1.8 / norm ** 2)
+    assert op.check_inputs(k.cuda(), beta.cuda()) <= 2.0
+    o_ref, s_ref = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    o, sT = _run(op, q, k, v, g, beta, S0, frame_tokens=C, flags=CHUNKED)
+    eo, es = max_rel_err(o, o_ref), max_rel_err(sT, s_ref)
+    print(f"|k| = {norm}: readout max-rel {eo:.2e} rms {rms_rel_err(o, o_ref):.2e}, final state max-rel {es:.2e}")
+    assert eo <= 2e-2 and es <= 2e-2
+    with pytest.raises(ValueError, match="unstable"):
+        op.check_inputs((k.float() * 2.0).cuda(), torch.ones_like(beta).cuda())
 
 
 @pytest.fixture(scope="module")
@@ -554,3 +669,66 @@ def test_full_size_paths_agree(op, echonet_batch):
     o, sT = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 49)
     o_r, s_r = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 49, RECURRENT)
     assert max_rel_err(o, o_r) <= 2e-2 and max_rel_err(sT, s_r) <= 2e-2
+
+
+def _device_batch(B, T, H, K, V, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=g, device="cuda", dtype=torch.float32)
+    l2 = lambda x: torch.nn.functional.normalize(x, dim=-1)
+    q = l2(rn(B, T, H, K)).bfloat16()
+    k = l2(rn(B, T, H, K)).bfloat16()
+    v = rn(B, T, H, V).bfloat16()
+    return q, k, v, torch.nn.functional.logsigmoid(rn(B, T, H) + 4.0), torch.sigmoid(rn(B, T, H)), 0.1 * rn(B, H, K, V)
+
+
+def _check_clips(o, sT, batch, clips, c_oracle, C, what):
+    q, k, v, g, beta, S0 = batch
+    worst = 0.0
+    for b in clips:
+        sl = slice(b, b + 1)
+        o_ref, s_ref = c_oracle.gdr_recurrent_c(q[sl].cpu(), k[sl].cpu(), v[sl].cpu(), g[sl].cpu(), beta[sl].cpu(), None, S0[sl].cpu())
+        _assert_per_chain(o[sl].float().cpu(), o_ref, sT[sl].cpu(), s_ref, 2e-2, (what, b))
+        worst = max(worst, float(per_frame_max_rel(o[sl].float().cpu(), o_ref, C).max()))
+    return worst
+
+
+def test_full_size_camus_vs_oracle(op, c_oracle):
+    """BASELINE configs[2]: 32 clips x 20 frames x 1024 tokens (256 x 256 frames, stride 8), 8 heads -- the whole batch on the
+    GPU, 2 clips x 8 heads against the C oracle, per chain."""
+    batch = _device_batch(32, 20 * 1024, 8, 64, 256, 2222)
+    q, k, v, g, beta, S0 = batch
+    o, sT = op.gdr_lkva(q, k, v, g, beta, None, S0, True, 1024)
+    torch.cuda.synchronize()
+    assert op.plan(q, k, v, g, beta, frame_tokens=1024) == 1
+    worst = _check_clips(o, sT, batch, (0, 31), c_oracle, 1024, "camus")
+    print(f"configs[2] full size: worst per-frame readout max-rel {worst:.2e}")
+    o2, sT2 = op.gdr_lkva(q, k, v * 2, g, beta, None, S0 * 2, True, 1024)               # linearity: every chain, bit-exact
+    assert torch.equal(o2.float(), o.float() * 2) and torch.equal(sT2, sT * 2)
+
+
+def test_full_size_long_clips_two_chained_calls_vs_oracle(op, c_oracle):
+    """BASELINE configs[3] (one GPU's share): 64 clips x 256 frames x 49 tokens, 8 heads, run as TWO chained calls (frames
+    0-127, then 128-255 from the first call's final state): 2 clips x 8 heads against the C oracle run over the whole
+    256-frame clip, per chain, with the error-growth curve over the frames."""
+    C, F = 49, 256
+    batch = _device_batch(64, F * C, 8, 64, 256, 3333)
+    q, k, v, g, beta, S0 = batch
+    cut = (F // 2) * C
+    oa, sa = op.gdr_lkva(q[:, :cut], k[:, :cut], v[:, :cut], g[:, :cut], beta[:, :cut], None, S0, True, C)
+    ob, sb = op.gdr_lkva(q[:, cut:], k[:, cut:], v[:, cut:], g[:, cut:], beta[:, cut:], None, sa, True, C)
+    torch.cuda.synchronize()
+    o = torch.cat([oa, ob], 1)
+    worst = 0.0
+    for b in (0, 63):
+        sl = slice(b, b + 1)
+        o_ref, s_ref = c_oracle.gdr_recurrent_c(q[sl].cpu(), k[sl].cpu(), v[sl].cpu(), g[sl].cpu(), beta[sl].cpu(), None, S0[sl].cpu())
+        _assert_per_chain(o[sl].float().cpu(), o_ref, sb[sl].cpu(), s_ref, 2e-2, ("long_clip", b))
+        curve = per_frame_max_rel(o[sl].float().cpu(), o_ref, C)
+        worst = max(worst, float(curve.max()))
+        # no drift: the last 32 frames are no worse than twice the first 32 (the state is a contraction, alpha < 1)
+        assert float(curve[-32:].max()) <= max(2.0 * float(curve[:32].max()), 1e-2), curve
+    print(f"configs[3] full size, two chained calls: worst per-frame readout max-rel {worst:.2e}")
+    o1, s1 = op.gdr_lkva(q, k, v, g, beta, None, S0, True, C, FRAME)                      # one call, frame-aligned chunks
+    oa2, sa2 = op.gdr_lkva(q[:, :cut], k[:, :cut], v[:, :cut], g[:, :cut], beta[:, :cut], None, S0, True, C, FRAME)
+    ob2, sb2 = op.gdr_lkva(q[:, cut:], k[:, cut:], v[:, cut:], g[:, cut:], beta[:, cut:], None, sa2, True, C, FRAME)
+    assert torch.equal(torch.cat([oa2, ob2], 1), o1) and torch.equal(sb2, s1)            # same chunking: bit-identical

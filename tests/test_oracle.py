@@ -13,13 +13,11 @@ import torch
 from oracle.gdr_ref import (chunk_schedule, gdr_backward_ref, gdr_chunk_ref, gdr_recurrent_ref, gdr_recurrent_varlen_ref, make_inputs,
                             max_rel_err)
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+import golden_util
+from oracle.gdr_ref import per_clip_errors, per_frame_max_rel, rms_rel_err
 
-
-def _load(path):
-    z = np.load(path)
-    t = {k: torch.from_numpy(z[k]) for k in ("q", "k", "v", "g", "beta", "s0", "o", "sT")}
-    return t, int(z["frame_tokens"])
+GOLDEN = golden_util.FP32
+_load = golden_util.load_fp32
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
@@ -40,7 +38,36 @@ def test_golden_chunked_and_c_port(path, c_oracle):
 
 
 def test_golden_present():
-    assert len(GOLDEN) >= 4
+    assert len(GOLDEN) >= 4 and len(golden_util.BF16) >= 6
+
+
+@pytest.mark.parametrize("path", golden_util.BF16, ids=golden_util.ids(golden_util.BF16))
+def test_bf16_golden_pins_the_oracle(path, c_oracle):
+    """fla-naive on bf16-ROUNDED q, k, v (the values the tcgen05 kernel consumes; 256-frame clip and 1024-token frames
+    included) against the C port (all cases) and the torch oracle (short cases)."""
+    q, k, v, g, beta, S0, rows, o_rows, sT_ref, C = golden_util.load_bf16(path)
+    o, sT = c_oracle.gdr_recurrent_c(q, k, v, g, beta, None, S0)
+    assert max_rel_err(o[:, rows], o_rows) < 2e-5 and max_rel_err(sT, sT_ref) < 2e-5
+    assert rms_rel_err(o[:, rows], o_rows) < 1e-5
+    if q.shape[1] <= 600:
+        o, sT = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+        assert max_rel_err(o[:, rows], o_rows) < 1e-5 and max_rel_err(sT, sT_ref) < 1e-5
+        o, sT = gdr_chunk_ref(q, k, v, g, beta, None, S0, frame_tokens=C)
+        assert max_rel_err(o[:, rows], o_rows) < 2e-5 and max_rel_err(sT, sT_ref) < 2e-5
+
+
+def test_error_metrics():
+    b = torch.zeros(2, 6, 2, 4)
+    b[0] = 100.0
+    b[1] = 0.01
+    a = b.clone()
+    a[1, 3, 1, 2] += 0.005                                   # a 50 % error on a small-magnitude chain
+    assert max_rel_err(a, b) < 1e-4                          # ... invisible to the whole-tensor metric
+    mo, ro, _ = per_clip_errors(a, b)
+    assert mo[1, 1] == pytest.approx(0.5) and mo[0].max() == 0 and ro[1, 1] > 0.05
+    curve = per_frame_max_rel(a, b, 2)
+    assert curve.shape == (3,) and curve[1] == pytest.approx(0.5) and curve[0] == 0 and curve[2] == 0
+    assert rms_rel_err(b, b) == 0 and rms_rel_err(2 * b, b) == pytest.approx(1.0)
 
 
 def test_fla_naive_cross_check():
