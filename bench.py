@@ -74,29 +74,21 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
-        self.rows = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                        "-lms", "50", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
-    def stop(self):
-        """Stop sampling and parse: rows of (epoch seconds, sm MHz, max sm MHz, power W, {reasons})."""
-        if self.rows is not None:
-            return
-        self.rows = []
-        if self.p is None:
-            return
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
+    def _parse(self):
+        """rows of (epoch seconds, sm MHz, max sm MHz, power W, {reasons}) written so far (the sampler keeps running)"""
         import datetime
-        for line in self.f.read().splitlines():
+        rows = []
+        try:
+            text = open(self.f.name).read()
+        except Exception:
+            return rows
+        for line in text.splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 10:
                 continue
@@ -107,14 +99,28 @@ class ClockSampler:
             except ValueError:
                 continue
             names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-            self.rows.append((ts, sm, mx, pw, {n for n, v in zip(names, c[6:10]) if v.lower().startswith("active")}))
-        self.f.close()
-        os.unlink(self.f.name)
+            rows.append((ts, sm, mx, pw, {n for n, v in zip(names, c[6:10]) if v.lower().startswith("active")}))
+        return rows
+
+    def stop(self):
+        if self.p is not None:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+            self.p = None
+        try:
+            self.f.close()
+            os.unlink(self.f.name)
+        except Exception:
+            pass
 
     def window(self, t0, t1):
         """{"sm_mhz": median, "sm_max_mhz", "reasons", "samples", "power_w_max"} of the samples with t0 <= t <= t1."""
-        self.stop()
-        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        if time.time() < t1 + 0.12:
+            time.sleep(0.12)                      # let the sample that closes the window reach the file
+        rows = [r for r in self._parse() if t0 - 0.05 <= r[0] <= t1 + 0.05]
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(rows), "seconds": round(t1 - t0, 3)}
         if rows:
             sm = sorted(r[1] for r in rows)
@@ -618,6 +624,8 @@ def main():
     if extra is not None:
         line["extra"] = extra
     print(json.dumps(line), flush=True)
+    if sampler is not None:
+        sampler.stop()
     if world > 1:
         dist.destroy_process_group()
 

@@ -72,6 +72,8 @@ def _warn_fallback(lib, p, what):
     """Loud, once per reason: an un-forced call that the tcgen05 kernel cannot take runs the fp32 CUDA-core kernel."""
     if p.flags & (_cabi.FLAG_FORCE_RECURRENT | _cabi.FLAG_FORCE_CHUNKED) or p.T == 0:
         return
+    if lib.gdkvm_gdr_plan(ctypes.byref(p)) != 0:         # the chunk kernel takes it, or the call is about to fail validation
+        return
     reason = lib.gdkvm_gdr_plan_reason(ctypes.byref(p)).decode()
     if reason and reason not in _warned_fallback:
         _warned_fallback.add(reason)
