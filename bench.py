@@ -442,7 +442,7 @@ def main():
     # sustained: the same step back to back for a few seconds straight after the burst (a box slows by several per cent
     # within seconds of load); the first and the last quarter are timed apart to show the drift
     sustained = None
-    if not args.no_extras and args.sustained_seconds > 0:
+    if args.sustained_seconds > 0:
         n_sus = max(args.steps, int(args.sustained_seconds * 1e3 / ms_step))
         n_q = max(1, n_sus // 4)
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(4)]

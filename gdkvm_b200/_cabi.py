@@ -20,7 +20,7 @@ def FLAG_SEGMENTS(n: int) -> int:
 EXPORTED_SYMBOLS = (
     "gdkvm_abi_version", "gdkvm_strerror", "gdkvm_last_cuda_error",
     "gdkvm_gdr_fwd", "gdkvm_gdr_fwd_varlen", "gdkvm_gdr_plan", "gdkvm_gdr_plan_segments", "gdkvm_gdr_plan_reason",
-    "gdkvm_launch_count", "gdkvm_l2norm_fwd",
+    "gdkvm_launch_count", "gdkvm_l2norm_fwd", "gdkvm_gdr_fwd_train", "gdkvm_gdr_chunk_states_bytes", "gdkvm_gdr_bwd",
 )
 
 
@@ -37,6 +37,21 @@ class GdkvmGdrParams(ctypes.Structure):
         ("K", ctypes.c_int32), ("V", ctypes.c_int32),
         ("frame_tokens", ctypes.c_int32), ("io_dtype", ctypes.c_int32), ("gate_dtype", ctypes.c_int32),
         ("scale", ctypes.c_float), ("reserved", ctypes.c_int32),
+    ]
+
+
+class GdkvmGdrBwdParams(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32), ("flags", ctypes.c_uint32),
+        ("q", ctypes.c_void_p), ("k", ctypes.c_void_p), ("v", ctypes.c_void_p), ("g", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+        ("d_o", ctypes.c_void_p), ("d_final_state", ctypes.c_void_p), ("chunk_states", ctypes.c_void_p),
+        ("dq", ctypes.c_void_p), ("dk", ctypes.c_void_p), ("dv", ctypes.c_void_p), ("dg", ctypes.c_void_p), ("dbeta", ctypes.c_void_p),
+        ("d_initial_state", ctypes.c_void_p),
+        ("q_stride", ctypes.c_int64 * 3), ("k_stride", ctypes.c_int64 * 3), ("v_stride", ctypes.c_int64 * 3),
+        ("do_stride", ctypes.c_int64 * 3), ("g_stride", ctypes.c_int64 * 3), ("beta_stride", ctypes.c_int64 * 3),
+        ("dq_stride", ctypes.c_int64 * 3), ("dk_stride", ctypes.c_int64 * 3), ("dv_stride", ctypes.c_int64 * 3),
+        ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("H", ctypes.c_int32), ("K", ctypes.c_int32), ("V", ctypes.c_int32),
+        ("io_dtype", ctypes.c_int32), ("gate_dtype", ctypes.c_int32), ("scale", ctypes.c_float),
     ]
 
 
@@ -73,6 +88,12 @@ def load() -> ctypes.CDLL:
             lib.gdkvm_l2norm_fwd.restype = ctypes.c_int
             lib.gdkvm_l2norm_fwd.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64,
                                              ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_void_p]
+            lib.gdkvm_gdr_fwd_train.restype = ctypes.c_int
+            lib.gdkvm_gdr_fwd_train.argtypes = [ctypes.POINTER(GdkvmGdrParams), ctypes.c_void_p, ctypes.c_void_p]
+            lib.gdkvm_gdr_chunk_states_bytes.restype = ctypes.c_int64
+            lib.gdkvm_gdr_chunk_states_bytes.argtypes = [ctypes.c_int32] * 5
+            lib.gdkvm_gdr_bwd.restype = ctypes.c_int
+            lib.gdkvm_gdr_bwd.argtypes = [ctypes.POINTER(GdkvmGdrBwdParams), ctypes.c_void_p]
             if lib.gdkvm_abi_version() != GDKVM_ABI_VERSION:
                 raise RuntimeError("libgdkvm_gdr.so ABI version mismatch; rebuild")
             _lib = lib

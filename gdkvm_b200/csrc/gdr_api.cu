@@ -164,6 +164,45 @@ int gdkvm_gdr_fwd_varlen(const GdkvmGdrParams* params, const void* cu_seqlens, i
     return GDKVM_OK;
 }
 
+int64_t gdkvm_gdr_chunk_states_bytes(int32_t B, int32_t T, int32_t H, int32_t K, int32_t V) {
+    if (B <= 0 || T < 0 || H <= 0 || K <= 0 || V <= 0) return 0;
+    return (int64_t)B * H * ((T + 63) / 64) * V * K * 2;
+}
+
+int gdkvm_gdr_fwd_train(const GdkvmGdrParams* params, void* chunk_states, void* cuda_stream) {
+    int rc = gdkvm::validate(params);
+    if (rc != GDKVM_OK) return rc;
+    if (params->flags & GDKVM_FLAG_FORCE_RECURRENT) return GDKVM_ERR_UNSUPPORTED;
+    if (!gdkvm::chunked_supports(*params) || (params->V != 128 && params->V != 256)) return params->T == 0 ? GDKVM_ERR_SHAPE : GDKVM_ERR_UNSUPPORTED;
+    if (chunk_states == nullptr) return GDKVM_ERR_NULL;
+    if (reinterpret_cast<uintptr_t>(chunk_states) & 15u) return GDKVM_ERR_ALIGN;
+    bool sm100 = false;
+    int ce = gdkvm::device_is_sm100(&sm100);
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    if (!sm100) return GDKVM_ERR_ARCH;
+    ce = gdkvm::launch_chunked(*params, reinterpret_cast<cudaStream_t>(cuda_stream), chunk_states);
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    return GDKVM_OK;
+}
+
+int gdkvm_gdr_bwd(const GdkvmGdrBwdParams* p, void* cuda_stream) {
+    if (p == nullptr) return GDKVM_ERR_NULL;
+    if (p->struct_size != sizeof(GdkvmGdrBwdParams)) return GDKVM_ERR_ABI;
+    if (p->io_dtype != GDKVM_F32 && p->io_dtype != GDKVM_BF16) return GDKVM_ERR_DTYPE;
+    if (p->gate_dtype != GDKVM_F32 && p->gate_dtype != GDKVM_BF16) return GDKVM_ERR_DTYPE;
+    if (p->B <= 0 || p->H <= 0 || p->T <= 0 || p->V <= 0 || p->K <= 0) return GDKVM_ERR_SHAPE;
+    if (!p->q || !p->k || !p->v || !p->g || !p->beta || !p->d_o || !p->chunk_states || !p->dq || !p->dk || !p->dv || !p->dg || !p->dbeta)
+        return GDKVM_ERR_NULL;
+    if (gdkvm::bwd_unsupported_reason(*p)[0] != '\0') return GDKVM_ERR_UNSUPPORTED;
+    bool sm100 = false;
+    int ce = gdkvm::device_is_sm100(&sm100);
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    if (!sm100) return GDKVM_ERR_ARCH;
+    ce = gdkvm::launch_bwd(*p, reinterpret_cast<cudaStream_t>(cuda_stream));
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    return GDKVM_OK;
+}
+
 int gdkvm_gdr_fwd(const GdkvmGdrParams* params, void* cuda_stream) {
     int rc = gdkvm::validate(params);
     if (rc != GDKVM_OK) return rc;

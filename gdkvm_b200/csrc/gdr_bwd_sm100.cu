@@ -1,0 +1,628 @@
+// Backward pass of the GDR/LKVA memory op on sm_100a (the upstream model is trained:
+// reference website/src/pages/[lang]/reprod/index.astro:238-252).
+//
+// Chunked reverse-mode differentiation of the WY/UT form (math: oracle/gdr_ref.py::gdr_chunk_backward_ref, which is
+// checked against autograd through the token recurrence in float64).  One CTA = one (clip, head) chain, walking its
+// 64-token chunks BACKWARDS in time with the state cotangent dS [64 x V] held in fp32 REGISTERS for the whole clip (the
+// mirror image of the forward kernel's S in TMEM).  The chunk-start states S_c come from the training forward
+// (gdkvm_gdr_fwd_train: the tcgen05 kernel also stores its bf16 operand copy Sb per chunk); everything else is recomputed
+// per chunk from q, k, v, g, beta: A, T = (I + A)^-1 (the forward kernel's in-register fp16 block solve, tri_solve.cuh),
+// W, Vn.  Per chunk, with e_i = exp(Gamma_i), gamma = e_last, D_ij = e_i / e_j (j <= i), P' = scale tril(Q K^T D),
+// Tb = T diag(beta), Tbe = T diag(beta e):
+//     W  = Tbe K                      Vn  = Tb V - W S                       dVn = diag(gamma / e) K dS' + P'^T dO
+//     dS = gamma dS' + (scale e Q)^T dO - W^T dVn                            dP' = tril(dO Vn^T)
+//     dQ = scale e (dO S^T) + (scale dP' D) K                                dW  = -dVn S^T
+//     dT = tril_strict[(dW K^T) diag(beta e) + (dVn V^T) diag(beta)]        dA  = -tril_strict(T^T dT T^T)
+//     dV = diag(beta) T^T dVn         dK  = (scale dP' D)^T Q + diag(gamma / e) Vn dS'^T + diag(beta e) T^T dW + (M + M^T) K,
+//     M  = dA diag_rows(beta) D       dbeta, dGamma = row / column sums of the same products; dg = reverse cumsum(dGamma)
+// About 63 products of 64 x 64 x 64 per chunk and chain, all on the legacy warp-level tensor path (mma.sync m16n8k16, bf16
+// in / fp32 out, ldmatrix fragments from padded shared-memory tiles): sixteen warps, each owning one 16 x 16 (or 16 x 32)
+// output tile of every product, so the per-tile partial results (dS, dP', dW, ...) stay in registers across the two
+// 128-column value halves.  The value dimension is streamed in halves of 128 columns through one set of tiles.
+//
+// Bound: HBM in principle (algorithmic bytes per token-head: q,k,v,do read + dq,dk,dv written + chunk state read =
+// 2 576 + 512 B); this first version is bound by its own instruction issue and exposed load latency.
+#include <mutex>
+
+#include "gdr_common.cuh"
+#include "sm100_ptx.cuh"
+#include "tri_solve.cuh"
+
+namespace gdkvm {
+namespace {
+
+using sm100::smem_u32;
+using sm100::sw128_offset;
+using sm100::pack_bf16;
+
+constexpr int kBwdThreads = 512;                 // 16 warps: 4 (row tiles) x 4 (column groups)
+constexpr int LD64 = 72, LD128 = 136;            // padded leading dimensions (elements): rows 16-byte aligned, ldmatrix conflict-free
+constexpr uint32_t SZ64 = 64 * LD64 * 2;         // 64 x 64 bf16 tile
+constexpr uint32_t SZ128 = 64 * LD128 * 2;       // 64 x 128 bf16 tile
+constexpr uint32_t SZS = 128 * LD64 * 2;         // chunk-start state half [128 values][64 key dims]
+// ---- shared memory map ----
+constexpr uint32_t oK = 0, oQ = oK + SZ64, oQe = oQ + SZ64, oT = oQe + SZ64, oTb = oT + SZ64, oP = oTb + SZ64, oKKD = oP + SZ64,
+                   oWn = oKKD + SZ64, oH = oWn + SZ64;
+constexpr uint32_t oV = oH + 8192, odO = oV + SZ128, oVn = odO + SZ128, odVn = oVn + SZ128, oS = odVn + SZ128, odSb = oS + SZS;
+constexpr uint32_t oF = odSb + SZ128;
+constexpr int kNumF = 6 * 64 + 8;                // Gam, E, Bt, Kd, dGam, dBt, misc
+constexpr uint32_t kBwdSmem = oF + kNumF * 4 + 16;
+// after the value halves the four big tiles are dead: the 64 x 64 operands of the tail live there
+constexpr uint32_t odW = oV, odPD = oV + SZ64, odT = oV + 2 * SZ64, oX = oV + 3 * SZ64, oM = oV + 4 * SZ64, oOutQ = oV + 5 * SZ64,
+                   oOutK = oV + 6 * SZ64;
+static_assert(oOutK + SZ64 <= oS, "tail operands must fit into the four value tiles");
+constexpr uint32_t oTbe = oVn;                   // T diag(beta e): only until W has been formed
+static_assert(kBwdSmem <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+// One warp: acc[NT][4] (a 16 x 8 NT tile at rows m0, columns n0) += A(m, k) B(k, n) for k in [k0, k1) (multiples of 16).
+//   TA = false: A stored row-major   mem[m][k] (leading dimension LDA);  TA = true: stored transposed mem[k][m]
+//   TB = false: B stored n-major     mem[n][k] (leading dimension LDB);  TB = true: stored k-major    mem[k][n]
+// Fragment layouts of mma.m16n8k16 (g = lane / 4, t = lane % 4): a0 (g, 2t) a1 (g + 8, 2t) a2 (g, 2t + 8) a3 (g + 8, 2t + 8);
+// b0 (k 2t, n g) b1 (k 2t + 8, n g); c0, c1 (g, 2t / 2t + 1) c2, c3 (g + 8, ..).
+template <int NT, bool TA, bool TB, int LDA, int LDB>
+__device__ __forceinline__ void wgemm(float (&acc)[NT][4], uint32_t A, int m0, uint32_t B, int n0, int k0, int k1, int lane) {
+    static_assert(NT % 2 == 0, "two n8 tiles per ldmatrix.x4");
+    const uint32_t a_lane = TA ? A + (uint32_t)((((lane & 7) + 8 * (lane >> 4)) * LDA + m0 + 8 * ((lane >> 3) & 1)) * 2)
+                               : A + (uint32_t)(((m0 + (lane & 15)) * LDA + 8 * (lane >> 4)) * 2);
+    const uint32_t b_lane = TB ? B + (uint32_t)((((lane & 7) + 8 * ((lane >> 3) & 1)) * LDB + n0 + 8 * (lane >> 4)) * 2)
+                               : B + (uint32_t)(((n0 + (lane & 7) + 8 * (lane >> 4)) * LDB + 8 * ((lane >> 3) & 1)) * 2);
+#pragma unroll 2
+    for (int k = k0; k < k1; k += 16) {
+        uint32_t a[4];
+        if (TA) ldsm4t(a, a_lane + (uint32_t)(k * LDA * 2)); else ldsm4(a, a_lane + (uint32_t)(k * 2));
+#pragma unroll
+        for (int nt = 0; nt < NT; nt += 2) {
+            uint32_t b[4];
+            if (TB) ldsm4t(b, b_lane + (uint32_t)((k * LDB + nt * 8) * 2)); else ldsm4(b, b_lane + (uint32_t)((nt * 8 * LDB + k) * 2));
+            mma16816(acc[nt], a, b[0], b[1]);
+            mma16816(acc[nt + 1], a, b[2], b[3]);
+        }
+    }
+}
+
+template <int NT>
+__device__ __forceinline__ void zero_acc(float (&acc)[NT][4]) {
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+}
+
+// accumulator tile -> bf16 row-major shared-memory tile (rows m0 + g / + 8, columns n0 + 8 nt + 2t): 32-bit stores, conflict-free
+template <int NT, int LD>
+__device__ __forceinline__ void store_tile(uint8_t* base, const float (&acc)[NT][4], int m0, int n0, int lane, float s = 1.f) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        *reinterpret_cast<uint32_t*>(base + ((m0 + g) * LD + n0 + nt * 8 + 2 * t) * 2) = pack_bf16(acc[nt][0] * s, acc[nt][1] * s);
+        *reinterpret_cast<uint32_t*>(base + ((m0 + g + 8) * LD + n0 + nt * 8 + 2 * t) * 2) = pack_bf16(acc[nt][2] * s, acc[nt][3] * s);
+    }
+}
+template <int LD>
+__device__ __forceinline__ void zero_tile16(uint8_t* base, int m0, int n0, int lane) {      // a 16 x 16 tile
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+        *reinterpret_cast<uint32_t*>(base + ((m0 + g) * LD + n0 + nt * 8 + 2 * t) * 2) = 0u;
+        *reinterpret_cast<uint32_t*>(base + ((m0 + g + 8) * LD + n0 + nt * 8 + 2 * t) * 2) = 0u;
+    }
+}
+
+__device__ __forceinline__ float2 bf2(const uint8_t* base, int row, int col, int ld) {      // two adjacent bf16 -> float2
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(base + (row * ld + col) * 2);
+    return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+// sum over the four lanes of a quad (the lanes that share an accumulator row)
+__device__ __forceinline__ float quad_sum(float x) {
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    return x;
+}
+// sum over the eight lanes that share accumulator columns (same lane % 4)
+__device__ __forceinline__ float col_sum(float x) {
+    x += __shfl_xor_sync(0xffffffffu, x, 4);
+    x += __shfl_xor_sync(0xffffffffu, x, 8);
+    x += __shfl_xor_sync(0xffffffffu, x, 16);
+    return x;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// rows [0, valid) x `cols` bf16 columns of a global tile (row stride in elements) -> padded shared tile; rows >= valid zero
+template <int LD>
+__device__ __forceinline__ void load_tile(uint8_t* smem, uint32_t saddr, const __nv_bfloat16* src, int64_t row_stride, int rows, int valid,
+                                          int cols, int tid) {
+    const int cpr = cols >> 3;                       // 16-byte chunks per row
+    for (int idx = tid; idx < rows * cpr; idx += kBwdThreads) {
+        const int r = idx / cpr, c = idx - r * cpr;
+        if (r < valid) cp_async16(saddr + (uint32_t)((r * LD + c * 8) * 2), src + (int64_t)r * row_stride + c * 8);
+        else *reinterpret_cast<uint4*>(smem + (r * LD + c * 8) * 2) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+template <int NH>
+__global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrBwdParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const uint32_t sb = smem_u32(smem);
+    float* sGam = reinterpret_cast<float*>(smem + oF);   // Gamma_i
+    float* sE = sGam + 64;                               // exp(Gamma_i)
+    float* sBt = sE + 64;                                // beta_i
+    float* sKd = sBt + 64;                               // gamma / e_i = exp(Gamma_last - Gamma_i)
+    float* sdGam = sKd + 64;                             // dGamma_i accumulators
+    float* sdBt = sdGam + 64;                            // dbeta_i accumulators
+    float* sMisc = sdBt + 64;                            // [0] sum_i (gamma / e_i) (dKh_i . k_i)   [1] <dS', S>
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2, m0 = 16 * wm, n64 = 16 * wn, n128 = 32 * wn;
+    const int chain = blockIdx.x, b = chain / p.H, h = chain - b * p.H;
+    const int T = p.T, V = p.V, NC = (T + 63) >> 6;
+    const float scale = p.scale;
+
+    const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(p.q) + (int64_t)b * p.q_stride[0] + (int64_t)h * p.q_stride[2];
+    const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(p.k) + (int64_t)b * p.k_stride[0] + (int64_t)h * p.k_stride[2];
+    const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(p.v) + (int64_t)b * p.v_stride[0] + (int64_t)h * p.v_stride[2];
+    const __nv_bfloat16* dog = reinterpret_cast<const __nv_bfloat16*>(p.d_o) + (int64_t)b * p.do_stride[0] + (int64_t)h * p.do_stride[2];
+    __nv_bfloat16* dqg = reinterpret_cast<__nv_bfloat16*>(p.dq) + (int64_t)b * p.dq_stride[0] + (int64_t)h * p.dq_stride[2];
+    __nv_bfloat16* dkg = reinterpret_cast<__nv_bfloat16*>(p.dk) + (int64_t)b * p.dk_stride[0] + (int64_t)h * p.dk_stride[2];
+    __nv_bfloat16* dvg = reinterpret_cast<__nv_bfloat16*>(p.dv) + (int64_t)b * p.dv_stride[0] + (int64_t)h * p.dv_stride[2];
+    const __nv_bfloat16* sg = reinterpret_cast<const __nv_bfloat16*>(p.chunk_states) + (int64_t)chain * NC * V * 64;
+    const int64_t g_off = (int64_t)b * p.g_stride[0] + (int64_t)h * p.g_stride[2];
+    const int64_t bt_off = (int64_t)b * p.beta_stride[0] + (int64_t)h * p.beta_stride[2];
+
+    // state cotangent dS [64 key dims x V], fp32, in registers: warp (wm, wn) owns rows 16 wm .. + 15, columns 32 wn .. + 31 of
+    // each 128-column half
+    float dS[NH][4][4];
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int col = hh * 128 + n128 + nt * 8 + 2 * t;
+            float2 lo = make_float2(0.f, 0.f), hi = lo;
+            if (p.d_final_state != nullptr && col < V) {
+                const float* src = p.d_final_state + (int64_t)chain * 64 * V + col;
+                lo = *reinterpret_cast<const float2*>(src + (int64_t)(m0 + g) * V);
+                hi = *reinterpret_cast<const float2*>(src + (int64_t)(m0 + g + 8) * V);
+            }
+            dS[hh][nt][0] = lo.x; dS[hh][nt][1] = lo.y; dS[hh][nt][2] = hi.x; dS[hh][nt][3] = hi.y;
+        }
+
+    for (int c = NC - 1; c >= 0; --c) {
+        const int t0 = c << 6, valid = min(64, T - t0);
+        // ---- loads: K, Q and the first value half (V, dO, chunk-start state) ----
+        load_tile<LD64>(smem + oK, sb + oK, kg + (int64_t)t0 * p.k_stride[1], p.k_stride[1], 64, valid, 64, tid);
+        load_tile<LD64>(smem + oQ, sb + oQ, qg + (int64_t)t0 * p.q_stride[1], p.q_stride[1], 64, valid, 64, tid);
+        load_tile<LD128>(smem + oV, sb + oV, vg + (int64_t)t0 * p.v_stride[1], p.v_stride[1], 64, valid, 128, tid);
+        load_tile<LD128>(smem + odO, sb + odO, dog + (int64_t)t0 * p.do_stride[1], p.do_stride[1], 64, valid, 128, tid);
+        load_tile<LD64>(smem + oS, sb + oS, sg + (int64_t)c * V * 64, 64, 128, min(128, V), 64, tid);
+        if (warp == 0) {        // gates of the chunk: lane l holds tokens 2l, 2l + 1; pad tokens g = 0, beta = 0 (exact no-ops)
+            float gv[2], bv[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int tok = 2 * lane + e;
+                gv[e] = 0.f; bv[e] = 0.f;
+                if (tok < valid) {
+                    gv[e] = load_gate(p.g, g_off + (int64_t)(t0 + tok) * p.g_stride[1], p.gate_dtype);
+                    bv[e] = load_gate(p.beta, bt_off + (int64_t)(t0 + tok) * p.beta_stride[1], p.gate_dtype);
+                }
+            }
+            float s = gv[0] + gv[1];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const float u = __shfl_up_sync(0xffffffffu, s, off);
+                if (lane >= off) s += u;
+            }
+            const float G1 = s, G0 = s - gv[1], Gl = __shfl_sync(0xffffffffu, s, 31);
+            *reinterpret_cast<float2*>(sGam + 2 * lane) = make_float2(G0, G1);
+            *reinterpret_cast<float2*>(sE + 2 * lane) = make_float2(__expf(G0), __expf(G1));
+            *reinterpret_cast<float2*>(sBt + 2 * lane) = make_float2(bv[0], bv[1]);
+            *reinterpret_cast<float2*>(sKd + 2 * lane) = make_float2(__expf(Gl - G0), __expf(Gl - G1));
+        } else if (warp == 1) {
+            sdGam[lane] = 0.f; sdGam[lane + 32] = 0.f; sdBt[lane] = 0.f; sdBt[lane + 32] = 0.f;
+            if (lane < 8) sMisc[lane] = 0.f;
+        }
+        cp_async_commit_wait();
+        __syncthreads();
+        const float gamma = sE[63];
+
+        // ---- K K^T, Q K^T -> A (fp16, the solve's layout), K K^T D (bf16), P' = scale tril(Q K^T D) (bf16); Qe = scale e Q ----
+        {
+            uint8_t* sH = smem + oH;
+            if (wn > wm) {        // tile strictly above the diagonal: everything masked
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int r8 = 0; r8 < 2; ++r8) {
+                        const int i = m0 + g + 8 * r8, j = n64 + nt * 8 + 2 * t;
+                        *reinterpret_cast<uint32_t*>(sH + sw128_offset(i, j >> 3) + (j & 7) * 2) = 0u;
+                    }
+                zero_tile16<LD64>(smem + oKKD, m0, n64, lane);
+                zero_tile16<LD64>(smem + oP, m0, n64, lane);
+            } else {
+                float kk[2][4], qk[2][4];
+                zero_acc(kk); zero_acc(qk);
+                wgemm<2, false, false, LD64, LD64>(kk, sb + oK, m0, sb + oK, n64, 0, 64, lane);
+                wgemm<2, false, false, LD64, LD64>(qk, sb + oQ, m0, sb + oK, n64, 0, 64, lane);
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int r8 = 0; r8 < 2; ++r8) {
+                        const int i = m0 + g + 8 * r8, j = n64 + nt * 8 + 2 * t;
+                        const float gi = sGam[i], bi = sBt[i];
+                        const float d0 = j <= i ? __expf(gi - sGam[j]) : 0.f, d1 = j + 1 <= i ? __expf(gi - sGam[j + 1]) : 0.f;
+                        const float k0v = j < i ? kk[nt][2 * r8] * d0 : 0.f, k1v = j + 1 < i ? kk[nt][2 * r8 + 1] * d1 : 0.f;
+                        *reinterpret_cast<uint32_t*>(sH + sw128_offset(i, j >> 3) + (j & 7) * 2) = tri::pack_f16(bi * k0v, bi * k1v);
+                        *reinterpret_cast<uint32_t*>(smem + oKKD + (i * LD64 + j) * 2) = pack_bf16(k0v, k1v);
+                        *reinterpret_cast<uint32_t*>(smem + oP + (i * LD64 + j) * 2) = pack_bf16(scale * qk[nt][2 * r8] * d0, scale * qk[nt][2 * r8 + 1] * d1);
+                    }
+            }
+            {   // Qe = scale e_i Q: thread = (row, 16-byte chunk)
+                const int r = tid >> 3, ch = tid & 7;
+                const uint4 x = *reinterpret_cast<const uint4*>(smem + oQ + (r * LD64 + ch * 8) * 2);
+                const float f = scale * sE[r];
+                auto sc = [&](uint32_t w) { return pack_bf16(__uint_as_float(w << 16) * f, __uint_as_float(w & 0xffff0000u) * f); };
+                *reinterpret_cast<uint4*>(smem + oQe + (r * LD64 + ch * 8) * 2) = make_uint4(sc(x.x), sc(x.y), sc(x.z), sc(x.w));
+            }
+        }
+        __syncthreads();
+        // ---- T = (I + A)^-1 (fp16, in place in H) ----
+        if (warp < 2) tri::solve_levels01(smem + oH, sb + oH, warp, lane);
+        __syncthreads();
+        if (warp < 4) tri::solve_level2(sb + oH, warp, lane, 5);
+        __syncthreads();
+        {   // H -> T, Tb = T diag(beta), Tbe = T diag(beta e) as bf16 row-major tiles: thread = (row, 16-byte chunk)
+            const int r = tid >> 3, ch = tid & 7;
+            const uint4 hx = *reinterpret_cast<const uint4*>(smem + oH + sw128_offset(r, ch));
+            const uint32_t w[4] = {hx.x, hx.y, hx.z, hx.w};
+            uint32_t o0[4], o1[4], o2[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 x = tri::unpack_f16(w[e]);
+                const int j = ch * 8 + 2 * e;
+                const float b0 = sBt[j], b1 = sBt[j + 1], e0 = sE[j], e1 = sE[j + 1];
+                o0[e] = pack_bf16(x.x, x.y);
+                o1[e] = pack_bf16(x.x * b0, x.y * b1);
+                o2[e] = pack_bf16(x.x * b0 * e0, x.y * b1 * e1);
+            }
+            *reinterpret_cast<uint4*>(smem + oT + (r * LD64 + ch * 8) * 2) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+            *reinterpret_cast<uint4*>(smem + oTb + (r * LD64 + ch * 8) * 2) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+            *reinterpret_cast<uint4*>(smem + oTbe + (r * LD64 + ch * 8) * 2) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+        }
+        __syncthreads();
+        {   // Wn = -W = -Tbe K   (T is lower triangular: k < m0 + 16)
+            float w[2][4];
+            zero_acc(w);
+            wgemm<2, false, true, LD64, LD64>(w, sb + oTbe, m0, sb + oK, n64, 0, m0 + 16, lane);
+            store_tile<2, LD64>(smem + oWn, w, m0, n64, lane, -1.f);
+        }
+        __syncthreads();
+
+        // partial results of the chunk that are sums over the value dimension (kept in registers across the halves)
+        float dP[2][4], G2[2][4], dQS[2][4], dWa[2][4], dKh[2][4];
+        zero_acc(dP); zero_acc(G2); zero_acc(dQS); zero_acc(dWa); zero_acc(dKh);
+
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+            if (hh > 0) {        // second value half through the same tiles
+                load_tile<LD128>(smem + oV, sb + oV, vg + (int64_t)t0 * p.v_stride[1] + 128, p.v_stride[1], 64, valid, 128, tid);
+                load_tile<LD128>(smem + odO, sb + odO, dog + (int64_t)t0 * p.do_stride[1] + 128, p.do_stride[1], 64, valid, 128, tid);
+                load_tile<LD64>(smem + oS, sb + oS, sg + ((int64_t)c * V + 128) * 64, 64, 128, 128, 64, tid);
+                cp_async_commit_wait();
+                __syncthreads();
+            }
+            {   // bf16 copy of dS' (this half) as an MMA operand; <dS', S> for the gate gradient
+                float acc = 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                    for (int r8 = 0; r8 < 2; ++r8) {
+                        const int kd = m0 + g + 8 * r8, vc = n128 + nt * 8 + 2 * t;
+                        *reinterpret_cast<uint32_t*>(smem + odSb + (kd * LD128 + vc) * 2) = pack_bf16(dS[hh][nt][2 * r8], dS[hh][nt][2 * r8 + 1]);
+                        const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(smem + oS);
+                        acc += dS[hh][nt][2 * r8] * __bfloat162float(sp[vc * LD64 + kd]) + dS[hh][nt][2 * r8 + 1] * __bfloat162float(sp[(vc + 1) * LD64 + kd]);
+                    }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                if (lane == 0) atomicAdd(&sMisc[1], acc);
+            }
+            __syncthreads();
+            {   // Vn = Tb V + Wn S  (rows i = m0.., columns n128..)
+                float a[4][4];
+                zero_acc(a);
+                wgemm<4, false, true, LD64, LD128>(a, sb + oTb, m0, sb + oV, n128, 0, m0 + 16, lane);
+                wgemm<4, false, false, LD64, LD64>(a, sb + oWn, m0, sb + oS, n128, 0, 64, lane);
+                store_tile<4, LD128>(smem + oVn, a, m0, n128, lane);
+            }
+            {   // dVn = diag(gamma / e) K dS' + P'^T dO
+                float a[4][4];
+                zero_acc(a);
+                wgemm<4, false, true, LD64, LD128>(a, sb + oK, m0, sb + odSb, n128, 0, 64, lane);
+                const float f0 = sKd[m0 + g], f1 = sKd[m0 + g + 8];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) { a[nt][0] *= f0; a[nt][1] *= f0; a[nt][2] *= f1; a[nt][3] *= f1; }
+                wgemm<4, true, true, LD64, LD128>(a, sb + oP, m0, sb + odO, n128, m0, 64, lane);
+                store_tile<4, LD128>(smem + odVn, a, m0, n128, lane);
+            }
+            __syncthreads();
+            // dS = gamma dS' + Qe^T dO + Wn^T dVn
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) dS[hh][nt][e] *= gamma;
+            wgemm<4, true, true, LD64, LD128>(dS[hh], sb + oQe, m0, sb + odO, n128, 0, 64, lane);
+            wgemm<4, true, true, LD64, LD128>(dS[hh], sb + oWn, m0, sb + odVn, n128, 0, 64, lane);
+            if (wn <= wm) {      // lower-triangular outputs
+                wgemm<2, false, false, LD128, LD128>(dP, sb + odO, m0, sb + oVn, n64, 0, 128, lane);     // dP' += dO Vn^T
+                wgemm<2, false, false, LD128, LD128>(G2, sb + odVn, m0, sb + oV, n64, 0, 128, lane);     // G2  += dVn V^T
+            }
+            wgemm<2, false, true, LD128, LD64>(dQS, sb + odO, m0, sb + oS, n64, 0, 128, lane);           // dO S^T
+            wgemm<2, false, true, LD128, LD64>(dWa, sb + odVn, m0, sb + oS, n64, 0, 128, lane);          // dVn S^T  (= -dW)
+            wgemm<2, false, false, LD128, LD128>(dKh, sb + oVn, m0, sb + odSb, n64, 0, 128, lane);       // Vn dS'^T
+            __syncthreads();
+            {   // dV = diag(beta) T^T dVn, written over V in place (each thread reads exactly the V elements it overwrites);
+                // dbeta_j += (T^T dVn)_j . v_j
+                float a[4][4];
+                zero_acc(a);
+                wgemm<4, true, true, LD64, LD128>(a, sb + oT, m0, sb + odVn, n128, m0, 64, lane);
+                float d0 = 0.f, d1 = 0.f;
+                const float b0 = sBt[m0 + g], b1 = sBt[m0 + g + 8];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int vc = n128 + nt * 8 + 2 * t;
+                    const float2 v0 = bf2(smem + oV, m0 + g, vc, LD128), v1 = bf2(smem + oV, m0 + g + 8, vc, LD128);
+                    d0 += a[nt][0] * v0.x + a[nt][1] * v0.y;
+                    d1 += a[nt][2] * v1.x + a[nt][3] * v1.y;
+                    *reinterpret_cast<uint32_t*>(smem + oV + ((m0 + g) * LD128 + vc) * 2) = pack_bf16(a[nt][0] * b0, a[nt][1] * b0);
+                    *reinterpret_cast<uint32_t*>(smem + oV + ((m0 + g + 8) * LD128 + vc) * 2) = pack_bf16(a[nt][2] * b1, a[nt][3] * b1);
+                }
+                d0 = quad_sum(d0); d1 = quad_sum(d1);
+                if (t == 0) { atomicAdd(&sdBt[m0 + g], d0); atomicAdd(&sdBt[m0 + g + 8], d1); }
+            }
+            __syncthreads();
+            {   // dV half -> global (16-byte stores, valid rows only)
+                const int cols = min(128, V - hh * 128) >> 3;
+                for (int idx = tid; idx < 64 * 16; idx += kBwdThreads) {
+                    const int r = idx >> 4, ch = idx & 15;
+                    if (r < valid && ch < cols)
+                        *reinterpret_cast<uint4*>(dvg + (int64_t)(t0 + r) * p.dv_stride[1] + hh * 128 + ch * 8) =
+                            *reinterpret_cast<const uint4*>(smem + oV + (r * LD128 + ch * 8) * 2);
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- tail: the 64 x 64 quantities ----
+        store_tile<2, LD64>(smem + odW, dWa, m0, n64, lane, -1.f);                                    // dW = -(dVn S^T)
+        if (wn <= wm) {   // dP' -> dPD = scale dP' D (operand), dGamma += rowsum(dP P) - colsum(dP P)
+            float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int j = n64 + nt * 8 + 2 * t;
+                float cs0 = 0.f, cs1 = 0.f;
+#pragma unroll
+                for (int r8 = 0; r8 < 2; ++r8) {
+                    const int i = m0 + g + 8 * r8;
+                    const float gi = sGam[i];
+                    const float d0 = j <= i ? __expf(gi - sGam[j]) : 0.f, d1 = j + 1 <= i ? __expf(gi - sGam[j + 1]) : 0.f;
+                    const float2 pp = bf2(smem + oP, i, j, LD64);
+                    const float x0 = dP[nt][2 * r8] * pp.x, x1 = dP[nt][2 * r8 + 1] * pp.y;
+                    if (r8 == 0) rs0 += x0 + x1; else rs1 += x0 + x1;
+                    cs0 += x0; cs1 += x1;
+                    *reinterpret_cast<uint32_t*>(smem + odPD + (i * LD64 + j) * 2) = pack_bf16(scale * dP[nt][2 * r8] * d0, scale * dP[nt][2 * r8 + 1] * d1);
+                }
+                cs0 = col_sum(cs0); cs1 = col_sum(cs1);
+                if (g == 0) { atomicAdd(&sdGam[j], -cs0); atomicAdd(&sdGam[j + 1], -cs1); }
+            }
+            rs0 = quad_sum(rs0); rs1 = quad_sum(rs1);
+            if (t == 0) { atomicAdd(&sdGam[m0 + g], rs0); atomicAdd(&sdGam[m0 + g + 8], rs1); }
+        } else {
+            zero_tile16<LD64>(smem + odPD, m0, n64, lane);
+        }
+        __syncthreads();
+        float accK[2][4];
+        {   // dQ = scale e (dO S^T) + dPD K;  dGamma_i += scale e_i q_i . (dO S^T)_i
+            const float f0 = scale * sE[m0 + g], f1 = scale * sE[m0 + g + 8];
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int kc = n64 + nt * 8 + 2 * t;
+                const float2 q0 = bf2(smem + oQ, m0 + g, kc, LD64), q1 = bf2(smem + oQ, m0 + g + 8, kc, LD64);
+                d0 += dQS[nt][0] * q0.x + dQS[nt][1] * q0.y;
+                d1 += dQS[nt][2] * q1.x + dQS[nt][3] * q1.y;
+                dQS[nt][0] *= f0; dQS[nt][1] *= f0; dQS[nt][2] *= f1; dQS[nt][3] *= f1;
+            }
+            d0 = quad_sum(d0); d1 = quad_sum(d1);
+            if (t == 0) { atomicAdd(&sdGam[m0 + g], f0 * d0); atomicAdd(&sdGam[m0 + g + 8], f1 * d1); }
+            wgemm<2, false, true, LD64, LD64>(dQS, sb + odPD, m0, sb + oK, n64, 0, m0 + 16, lane);
+            store_tile<2, LD64>(smem + oOutQ, dQS, m0, n64, lane);
+        }
+        {   // dBt = T^T dW (rows j);  dbeta_j += e_j (dBt_j . k_j);  dGamma_j += beta_j e_j (dBt_j . k_j)
+            // dKh epilogue: dGamma_i -= (gamma / e_i) (dKh_i . k_i), and the same sum goes to dGamma_last
+            float bB[2][4];
+            zero_acc(bB);
+            wgemm<2, true, true, LD64, LD64>(bB, sb + oT, m0, sb + odW, n64, m0, 64, lane);
+            float d0 = 0.f, d1 = 0.f, h0 = 0.f, h1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int kc = n64 + nt * 8 + 2 * t;
+                const float2 k0v = bf2(smem + oK, m0 + g, kc, LD64), k1v = bf2(smem + oK, m0 + g + 8, kc, LD64);
+                d0 += bB[nt][0] * k0v.x + bB[nt][1] * k0v.y;
+                d1 += bB[nt][2] * k1v.x + bB[nt][3] * k1v.y;
+                h0 += dKh[nt][0] * k0v.x + dKh[nt][1] * k0v.y;
+                h1 += dKh[nt][2] * k1v.x + dKh[nt][3] * k1v.y;
+            }
+            d0 = quad_sum(d0); d1 = quad_sum(d1); h0 = quad_sum(h0); h1 = quad_sum(h1);
+            const float e0 = sE[m0 + g], e1 = sE[m0 + g + 8], b0 = sBt[m0 + g], b1 = sBt[m0 + g + 8];
+            const float kd0 = sKd[m0 + g], kd1 = sKd[m0 + g + 8];
+            if (t == 0) {
+                atomicAdd(&sdBt[m0 + g], e0 * d0); atomicAdd(&sdBt[m0 + g + 8], e1 * d1);
+                atomicAdd(&sdGam[m0 + g], b0 * e0 * d0 - kd0 * h0); atomicAdd(&sdGam[m0 + g + 8], b1 * e1 * d1 - kd1 * h1);
+                atomicAdd(&sMisc[0], kd0 * h0 + kd1 * h1);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                accK[nt][0] = kd0 * dKh[nt][0] + b0 * e0 * bB[nt][0]; accK[nt][1] = kd0 * dKh[nt][1] + b0 * e0 * bB[nt][1];
+                accK[nt][2] = kd1 * dKh[nt][2] + b1 * e1 * bB[nt][2]; accK[nt][3] = kd1 * dKh[nt][3] + b1 * e1 * bB[nt][3];
+            }
+        }
+        if (wn <= wm) {   // dT_ij = beta_j (e_j (dW K^T)_ij + G2_ij), strictly lower
+            float g1[2][4];
+            zero_acc(g1);
+            wgemm<2, false, false, LD64, LD64>(g1, sb + odW, m0, sb + oK, n64, 0, 64, lane);
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                for (int r8 = 0; r8 < 2; ++r8) {
+                    const int i = m0 + g + 8 * r8, j = n64 + nt * 8 + 2 * t;
+                    const float x0 = j < i ? sBt[j] * (sE[j] * g1[nt][2 * r8] + G2[nt][2 * r8]) : 0.f;
+                    const float x1 = j + 1 < i ? sBt[j + 1] * (sE[j + 1] * g1[nt][2 * r8 + 1] + G2[nt][2 * r8 + 1]) : 0.f;
+                    *reinterpret_cast<uint32_t*>(smem + odT + (i * LD64 + j) * 2) = pack_bf16(x0, x1);
+                }
+        } else {
+            zero_tile16<LD64>(smem + odT, m0, n64, lane);
+        }
+        __syncthreads();
+        if (wn <= wm) {   // X = T^T dT (lower part)
+            float x[2][4];
+            zero_acc(x);
+            wgemm<2, true, true, LD64, LD64>(x, sb + oT, m0, sb + odT, n64, m0, 64, lane);
+            store_tile<2, LD64>(smem + oX, x, m0, n64, lane);
+        } else {
+            zero_tile16<LD64>(smem + oX, m0, n64, lane);
+        }
+        __syncthreads();
+        if (wn <= wm) {   // dA = -X T^T (strictly lower);  M = dA diag_rows(beta) D;  dbeta, dGamma from dA . (K K^T D)
+            float a[2][4];
+            zero_acc(a);
+            wgemm<2, false, false, LD64, LD64>(a, sb + oX, m0, sb + oT, n64, 0, n64 + 16, lane);
+            float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 2; ++nt) {
+                const int j = n64 + nt * 8 + 2 * t;
+                float cs0 = 0.f, cs1 = 0.f;
+#pragma unroll
+                for (int r8 = 0; r8 < 2; ++r8) {
+                    const int i = m0 + g + 8 * r8;
+                    const float gi = sGam[i], bi = sBt[i];
+                    const float d0 = j < i ? __expf(gi - sGam[j]) : 0.f, d1 = j + 1 < i ? __expf(gi - sGam[j + 1]) : 0.f;
+                    const float a0 = j < i ? -a[nt][2 * r8] : 0.f, a1 = j + 1 < i ? -a[nt][2 * r8 + 1] : 0.f;
+                    const float2 kd = bf2(smem + oKKD, i, j, LD64);
+                    const float r0 = a0 * kd.x, r1 = a1 * kd.y;
+                    if (r8 == 0) rs0 += r0 + r1; else rs1 += r0 + r1;
+                    cs0 += bi * r0; cs1 += bi * r1;
+                    *reinterpret_cast<uint32_t*>(smem + oM + (i * LD64 + j) * 2) = pack_bf16(a0 * bi * d0, a1 * bi * d1);
+                }
+                cs0 = col_sum(cs0); cs1 = col_sum(cs1);
+                if (g == 0) { atomicAdd(&sdGam[j], -cs0); atomicAdd(&sdGam[j + 1], -cs1); }
+            }
+            rs0 = quad_sum(rs0); rs1 = quad_sum(rs1);
+            if (t == 0) {
+                atomicAdd(&sdBt[m0 + g], rs0); atomicAdd(&sdBt[m0 + g + 8], rs1);
+                atomicAdd(&sdGam[m0 + g], sBt[m0 + g] * rs0); atomicAdd(&sdGam[m0 + g + 8], sBt[m0 + g + 8] * rs1);
+            }
+        } else {
+            zero_tile16<LD64>(smem + oM, m0, n64, lane);
+        }
+        __syncthreads();
+        // dK = diag(gamma / e) dKh + diag(beta e) dBt (accK) + dPD^T Q + M K + M^T K
+        wgemm<2, true, true, LD64, LD64>(accK, sb + odPD, m0, sb + oQ, n64, m0, 64, lane);
+        wgemm<2, false, true, LD64, LD64>(accK, sb + oM, m0, sb + oK, n64, 0, m0 + 16, lane);
+        wgemm<2, true, true, LD64, LD64>(accK, sb + oM, m0, sb + oK, n64, m0, 64, lane);
+        store_tile<2, LD64>(smem + oOutK, accK, m0, n64, lane);
+        __syncthreads();
+        {   // dq, dk tiles -> global; dg = reverse cumsum of dGamma; dbeta
+            const int r = tid >> 3, ch = tid & 7;
+            if (r < valid) {
+                *reinterpret_cast<uint4*>(dqg + (int64_t)(t0 + r) * p.dq_stride[1] + ch * 8) = *reinterpret_cast<const uint4*>(smem + oOutQ + (r * LD64 + ch * 8) * 2);
+                *reinterpret_cast<uint4*>(dkg + (int64_t)(t0 + r) * p.dk_stride[1] + ch * 8) = *reinterpret_cast<const uint4*>(smem + oOutK + (r * LD64 + ch * 8) * 2);
+            }
+            if (warp == 0) {
+                float x0 = sdGam[2 * lane], x1 = sdGam[2 * lane + 1];
+                if (lane == 31) x1 += sMisc[0] + gamma * sMisc[1];       // terms of Gamma_last: K-hat and gamma S
+                float s = x0 + x1;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const float u = __shfl_down_sync(0xffffffffu, s, off);
+                    if (lane + off < 32) s += u;
+                }
+                const int64_t o0 = ((int64_t)b * T + t0 + 2 * lane) * p.H + h;
+                if (2 * lane < valid) { p.dg[o0] = s; p.dbeta[o0] = sdBt[2 * lane]; }
+                if (2 * lane + 1 < valid) { p.dg[o0 + p.H] = s - x0; p.dbeta[o0 + p.H] = sdBt[2 * lane + 1]; }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (p.d_initial_state != nullptr) {
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int col = hh * 128 + n128 + nt * 8 + 2 * t;
+                if (col < V) {
+                    float* dst = p.d_initial_state + (int64_t)chain * 64 * V + col;
+                    *reinterpret_cast<float2*>(dst + (int64_t)(m0 + g) * V) = make_float2(dS[hh][nt][0], dS[hh][nt][1]);
+                    *reinterpret_cast<float2*>(dst + (int64_t)(m0 + g + 8) * V) = make_float2(dS[hh][nt][2], dS[hh][nt][3]);
+                }
+            }
+    }
+}
+
+}  // namespace
+
+const char* bwd_unsupported_reason(const GdkvmGdrBwdParams& p) {
+    if (p.io_dtype != GDKVM_BF16) return "backward: q/k/v/do must be bf16 (the training forward keeps bf16 chunk states)";
+    if (p.K != 64) return "backward: d_k must be 64";
+    if (p.V != 128 && p.V != 256) return "backward: d_v must be 128 or 256";
+    const void* ptrs[8] = {p.q, p.k, p.v, p.d_o, p.dq, p.dk, p.dv, p.chunk_states};
+    for (const void* x : ptrs) if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0) return "backward: tensor bases must be 16-byte aligned";
+    for (int i = 0; i < 3; ++i) {
+        const int64_t s[7] = {p.q_stride[i], p.k_stride[i], p.v_stride[i], p.do_stride[i], p.dq_stride[i], p.dk_stride[i], p.dv_stride[i]};
+        for (int64_t x : s) if ((x * 2) % 16 != 0) return "backward: strides must be multiples of 16 bytes";
+    }
+    return "";
+}
+
+int launch_bwd(const GdkvmGdrBwdParams& p, cudaStream_t stream) {
+    static std::mutex mu;
+    static bool attr_ok[64];
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (dev < 0 || dev >= 64 || !attr_ok[dev]) {
+            e = cudaFuncSetAttribute(gdr_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem + 1024);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(gdr_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem + 1024);
+            if (e != cudaSuccess) return (int)e;
+            if (dev >= 0 && dev < 64) attr_ok[dev] = true;
+        }
+    }
+    const int chains = p.B * p.H;
+    if (p.V > 128) gdr_bwd_kernel<2><<<chains, kBwdThreads, kBwdSmem + 1024, stream>>>(p);
+    else gdr_bwd_kernel<1><<<chains, kBwdThreads, kBwdSmem + 1024, stream>>>(p);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+}  // namespace gdkvm

@@ -329,7 +329,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                  const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mo,
                  const GdkvmGdrParams p, const int C, const int F, const FastDiv div_cpf,
                  const int nseg, const int seg_chunks, float* __restrict__ xstate, int* __restrict__ xsync,
-                 const int* __restrict__ utab) {
+                 const int* __restrict__ utab, __nv_bfloat16* __restrict__ sdump) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-align inside the shared window with pointer arithmetic only (an integer round trip would
     // demote every access below from LDS/STS to generic LD/ST)
@@ -731,6 +731,16 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                             pk[16 + j] = pack_bf16(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1]));
                         }
                         tmem_st32(lane_addr + kColSb + hh * 32, pk);
+                        if (!kVar && sdump != nullptr) {
+                            // training forward: the bf16 chunk-start state (exactly the operand copy Sb) is kept for the backward
+                            // pass, [chain][chunk][value column][key dim] -- 128 contiguous bytes per thread
+                            const int m = (int)s_info[4] + n;
+                            if (m < nc_chain && vcol < V) {
+                                uint4* dst = reinterpret_cast<uint4*>(sdump + (((int64_t)s_info[1] * nc_chain + m) * V + vcol) * 64);
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                            }
+                        }
                         if (pre != 1.f) {      // slow path only
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
@@ -1181,13 +1191,14 @@ __global__ void __launch_bounds__(256) gdr_units_kernel(const IdxT* __restrict__
 
 }  // namespace
 
-int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
+int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream, void* chunk_states) {
     const DeviceCtx* dc = device_ctx();
     if (dc == nullptr) return (int)cudaErrorInvalidDevice;
     if (dc->attr_err != cudaSuccess) return (int)dc->attr_err;
     // frame-aligned chunks when frames are whole 64-token chunks (or when asked for); otherwise tile the
     // flat token stream: identical results (token-causal recurrence), no zero-padded rows to process
-    const bool flat = p.frame_tokens <= 0 || (p.flags & GDKVM_FLAG_FLAT_CHUNKS) ||
+    // (a training forward that keeps the chunk-start states always tiles the flat stream: the backward pass does too)
+    const bool flat = chunk_states != nullptr || p.frame_tokens <= 0 || (p.flags & GDKVM_FLAG_FLAT_CHUNKS) ||
                       (p.frame_tokens % 64 != 0 && !(p.flags & GDKVM_FLAG_FRAME_CHUNKS));
     const int C = flat ? p.T : p.frame_tokens;
     const int F = p.T / C;
@@ -1203,7 +1214,9 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
     // under capture the scratch becomes allocation / free nodes of the graph (stream-ordered allocator); without memory-pool
     // support a captured launch stays uncut
     const bool capturing = cap != cudaStreamCaptureStatusNone;
-    int nseg = (capturing && !dc->mempools) ? 1 : chunked_segments(p, dc->sms);
+    GdkvmGdrParams pf = p;
+    if (chunk_states != nullptr) { pf.flags |= GDKVM_FLAG_FLAT_CHUNKS; pf.flags &= ~GDKVM_FLAG_FRAME_CHUNKS; }
+    int nseg = (capturing && !dc->mempools) ? 1 : chunked_segments(pf, dc->sms);
     int seg_chunks = (nc + nseg - 1) / nseg;
     float* xstate = nullptr;
     int* xsync = nullptr;
@@ -1221,7 +1234,8 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream) {
         }
     }
     gdr_chunk_kernel<false><<<chains * nseg, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, C, F, FastDiv::make((unsigned)cpf),
-                                                                             nseg, seg_chunks, xstate, xsync, nullptr);
+                                                                             nseg, seg_chunks, xstate, xsync, nullptr,
+                                                                             reinterpret_cast<__nv_bfloat16*>(chunk_states));
     count_launch();
     const cudaError_t le = cudaGetLastError();
     if (ws != nullptr) cudaFreeAsync(ws, stream);
@@ -1271,7 +1285,7 @@ int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes,
                                                      p.initial_state, p.final_state);
     count_launch();
     gdr_chunk_kernel<true><<<max_entries * H, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, p.T, 1, FastDiv::make(1u), 0, 0, xstate,
-                                                                              xsync, utab);
+                                                                              xsync, utab, nullptr);
     count_launch();
     const cudaError_t le = cudaGetLastError();
     cudaFreeAsync(ws, stream);

@@ -11,7 +11,8 @@ namespace gdkvm {
 
 // Launchers (defined in gdr_recurrent.cu / gdr_chunked_sm100.cu). Return a cudaError_t as int.
 int launch_recurrent(const GdkvmGdrParams& p, cudaStream_t stream);
-int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream);
+// chunk_states != nullptr: training forward, also writes the bf16 chunk-start states [B*H][ceil(T/64)][V][K] (flat 64-token chunks)
+int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream, void* chunk_states = nullptr);
 // Packed variable-length sequences (q,k,v,o [1, T, H, *]; device-resident offsets cu[0..nseq], cu_bytes = 4 | 8; states [nseq, H, K, V])
 int launch_recurrent_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream);
 int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream);
@@ -22,6 +23,10 @@ bool chunked_supports(const GdkvmGdrParams& p);
 const char* chunked_unsupported_reason(const GdkvmGdrParams& p);
 // Time segments per chain the chunked kernel would use on a device with `sms` SMs (host-side schedule simulation).
 int chunked_segments(const GdkvmGdrParams& p, int sms);
+
+// Backward pass (gdr_bwd_sm100.cu)
+int launch_bwd(const GdkvmGdrBwdParams& p, cudaStream_t stream);
+const char* bwd_unsupported_reason(const GdkvmGdrBwdParams& p);
 
 void count_launch();
 

@@ -120,6 +120,21 @@ __device__ __forceinline__ void mbar_wait_inl(uint64_t* bar, uint32_t parity) {
 #else
     // one PTX block (labels are local to the braces): three instructions when the phase has already completed --
     // the kernel is instruction-issue bound and executes ~70 warp-level waits per chunk
+#if GDKVM_TRYWAIT_HINT_NS > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
+        "mov.u32 c, 0;\n"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %3;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "add.u32 c, c, 1;\n\t"
+        "setp.lt.u32 p, c, %2;\n\t"
+        "@p bra WAIT_LOOP;\n\t"
+        "trap;\n"
+        "WAIT_DONE:\n\t}\n"
+        ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)GDKVM_WAIT_POLLS), "r"((uint32_t)GDKVM_TRYWAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
         "mov.u32 c, 0;\n"
@@ -133,6 +148,7 @@ __device__ __forceinline__ void mbar_wait_inl(uint64_t* bar, uint32_t parity) {
         "WAIT_DONE:\n\t}\n"
         ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)GDKVM_WAIT_POLLS)
         : "memory");
+#endif
 #endif
 }
 

@@ -24,7 +24,7 @@ import torch
 
 from . import _cabi
 
-__all__ = ["gdr_lkva", "gdr_lkva_out", "gdr_lkva_varlen", "gdr_lkva_varlen_out", "check_inputs", "chunk_gated_delta_rule", "l2norm", "plan", "plan_reason",
+__all__ = ["gdr_lkva", "gdr_lkva_out", "train_unsupported_reason", "gdr_lkva_varlen", "gdr_lkva_varlen_out", "check_inputs", "chunk_gated_delta_rule", "l2norm", "plan", "plan_reason",
            "plan_segments", "launch_count"]
 
 _DT = {torch.float32: _cabi.GDKVM_F32, torch.bfloat16: _cabi.GDKVM_BF16}
@@ -166,6 +166,154 @@ def _gdr_lkva_fake(q, k, v, g, beta, scale=None, initial_state=None, output_fina
     return o, sT
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# training: forward that keeps the chunk-start states, backward kernel, autograd
+# ---------------------------------------------------------------------------------------------------------------------
+torch.library.define(
+    "gdkvm::gdr_lkva_train",
+    "(Tensor q, Tensor k, Tensor v, Tensor g, Tensor beta, float? scale=None, Tensor? initial_state=None, int flags=0) "
+    "-> (Tensor, Tensor, Tensor)",
+)
+torch.library.define(
+    "gdkvm::gdr_lkva_bwd",
+    "(Tensor q, Tensor k, Tensor v, Tensor g, Tensor beta, Tensor chunk_states, Tensor d_o, Tensor? d_final_state, float scale, "
+    "bool need_d_initial_state) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)",
+)
+
+
+def train_unsupported_reason(q, k, v) -> str:
+    """Why the training path (forward that keeps chunk states + backward kernel) cannot take these tensors ("" if it can)."""
+    if q.dtype != torch.bfloat16:
+        return "the backward pass takes bf16 q/k/v (fp32 I/O has no training path)"
+    if k.shape[-1] != 64 or v.shape[-1] not in (128, 256):
+        return "the backward pass is built for d_k = 64 and d_v in {128, 256}"
+    return ""
+
+
+@torch.library.impl("gdkvm::gdr_lkva_train", "CUDA")
+def _gdr_lkva_train_cuda(q, k, v, g, beta, scale=None, initial_state=None, flags=0):
+    _check(q, k, v, g, beta, initial_state)
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    why = train_unsupported_reason(q, k, v)
+    if why:
+        raise NotImplementedError(f"gdkvm_b200 training forward: {why}")
+    lib = _cabi.load()
+    if initial_state is not None:
+        initial_state = initial_state.contiguous()
+    o = torch.empty((B, T, H, V), dtype=q.dtype, device=q.device)
+    sT = torch.empty((B, H, K, V), dtype=torch.float32, device=q.device)
+    nbytes = lib.gdkvm_gdr_chunk_states_bytes(B, T, H, K, V)
+    cs = torch.empty((B * H, (T + 63) // 64, V, K), dtype=torch.bfloat16, device=q.device)
+    assert cs.numel() * 2 == nbytes
+    if T == 0:
+        sT.copy_(initial_state) if initial_state is not None else sT.zero_()
+        return o, sT, cs
+    if scale is None:
+        scale = 1.0 / math.sqrt(K)
+    p = _make_params(q, k, v, g, beta, o, initial_state, sT, scale, 0, flags & ~0xF)
+    with torch.cuda.device(q.device):
+        rc = lib.gdkvm_gdr_fwd_train(ctypes.byref(p), ctypes.c_void_p(cs.data_ptr()),
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        extra = f" (cudaError {lib.gdkvm_last_cuda_error()})" if rc == -7 else ""
+        raise RuntimeError(f"gdkvm_gdr_fwd_train: {_cabi.strerror(rc)}{extra}")
+    return o, sT, cs
+
+
+@torch.library.register_fake("gdkvm::gdr_lkva_train")
+def _gdr_lkva_train_fake(q, k, v, g, beta, scale=None, initial_state=None, flags=0):
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    return (q.new_empty((B, T, H, V)), q.new_empty((B, H, K, V), dtype=torch.float32),
+            q.new_empty((B * H, (T + 63) // 64, V, K), dtype=torch.bfloat16))
+
+
+@torch.library.impl("gdkvm::gdr_lkva_bwd", "CUDA")
+def _gdr_lkva_bwd_cuda(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale, need_d_initial_state):
+    _check(q, k, v, g, beta, None)
+    _same_device(q, chunk_states=chunk_states, d_o=d_o, d_final_state=d_final_state)
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    if d_o.shape != v.shape or d_o.dtype != q.dtype:
+        raise ValueError("d_o must have the shape and dtype of the readout")
+    if d_o.stride(-1) != 1:
+        d_o = d_o.contiguous()
+    if d_final_state is not None:
+        if d_final_state.shape != (B, H, K, V):
+            raise ValueError("d_final_state must be [B,H,K,V]")
+        d_final_state = d_final_state.to(torch.float32).contiguous()
+    dq, dk, dv = torch.empty_like(q, memory_format=torch.contiguous_format), torch.empty_like(k, memory_format=torch.contiguous_format), \
+        torch.empty_like(v, memory_format=torch.contiguous_format)
+    dg = torch.empty((B, T, H), dtype=torch.float32, device=q.device)
+    db = torch.empty((B, T, H), dtype=torch.float32, device=q.device)
+    ds0 = torch.empty((B, H, K, V) if need_d_initial_state else (0,), dtype=torch.float32, device=q.device)
+    if T == 0:
+        if need_d_initial_state:
+            ds0.copy_(d_final_state) if d_final_state is not None else ds0.zero_()
+        return dq, dk, dv, dg, db, ds0
+    lib = _cabi.load()
+    p = _cabi.GdkvmGdrBwdParams()
+    p.struct_size = ctypes.sizeof(_cabi.GdkvmGdrBwdParams)
+    p.q, p.k, p.v, p.g, p.beta = q.data_ptr(), k.data_ptr(), v.data_ptr(), g.data_ptr(), beta.data_ptr()
+    p.d_o = d_o.data_ptr()
+    p.d_final_state = d_final_state.data_ptr() if d_final_state is not None else None
+    p.chunk_states = chunk_states.data_ptr()
+    p.dq, p.dk, p.dv, p.dg, p.dbeta = dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dg.data_ptr(), db.data_ptr()
+    p.d_initial_state = ds0.data_ptr() if need_d_initial_state else None
+    p.q_stride, p.k_stride, p.v_stride, p.do_stride = _strides3(q), _strides3(k), _strides3(v), _strides3(d_o)
+    p.g_stride, p.beta_stride = _strides3(g), _strides3(beta)
+    p.dq_stride, p.dk_stride, p.dv_stride = _strides3(dq), _strides3(dk), _strides3(dv)
+    p.B, p.T, p.H, p.K, p.V = B, T, H, K, V
+    p.io_dtype, p.gate_dtype, p.scale = _DT[q.dtype], _DT[g.dtype], float(scale)
+    with torch.cuda.device(q.device):
+        rc = lib.gdkvm_gdr_bwd(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        extra = f" (cudaError {lib.gdkvm_last_cuda_error()})" if rc == -7 else ""
+        raise RuntimeError(f"gdkvm_gdr_bwd: {_cabi.strerror(rc)}{extra}")
+    return dq, dk, dv, dg, db, ds0
+
+
+@torch.library.register_fake("gdkvm::gdr_lkva_bwd")
+def _gdr_lkva_bwd_fake(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale, need_d_initial_state):
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    f32 = dict(dtype=torch.float32)
+    return (torch.empty_like(q), torch.empty_like(k), torch.empty_like(v), q.new_empty((B, T, H), **f32), q.new_empty((B, T, H), **f32),
+            q.new_empty((B, H, K, V) if need_d_initial_state else (0,), **f32))
+
+
+def _train_setup(ctx, inputs, output):
+    q, k, v, g, beta, scale, initial_state, flags = inputs
+    ctx.save_for_backward(q, k, v, g, beta, output[2])
+    ctx.scale = scale if scale is not None else 1.0 / math.sqrt(k.shape[-1])
+    ctx.has_s0 = initial_state is not None
+    ctx.set_materialize_grads(False)
+
+
+def _train_backward(ctx, d_o, d_sT, _d_cs):
+    q, k, v, g, beta, cs = ctx.saved_tensors
+    if d_o is None:
+        d_o = torch.zeros_like(v)
+    dq, dk, dv, dg, db, ds0 = torch.ops.gdkvm.gdr_lkva_bwd(q, k, v, g, beta, cs, d_o.to(q.dtype), d_sT, ctx.scale, ctx.has_s0)
+    return dq, dk, dv, dg.to(g.dtype), db.to(beta.dtype), None, (ds0 if ctx.has_s0 else None), None
+
+
+torch.library.register_autograd("gdkvm::gdr_lkva_train", _train_backward, setup_context=_train_setup)
+
+
+def _no_backward(name):
+    def backward(ctx, *grads):
+        raise NotImplementedError(
+            f"torch.ops.gdkvm.{name} has no backward formula: differentiate through gdkvm_b200.gdr_lkva / GDRMemory / "
+            "chunk_gated_delta_rule (they route a call that needs gradients to the training forward, bf16, d_k = 64, "
+            "d_v in {128, 256}); packed variable-length clips are forward-only")
+    return backward
+
+
+torch.library.register_autograd("gdkvm::gdr_lkva", _no_backward("gdr_lkva"))
+
+
 torch.library.define(
     "gdkvm::gdr_lkva_varlen",
     "(Tensor q, Tensor k, Tensor v, Tensor g, Tensor beta, Tensor cu_seqlens, float? scale=None, "
@@ -228,6 +376,8 @@ def _gdr_lkva_varlen_fake(q, k, v, g, beta, cu_seqlens, scale=None, initial_stat
     return q.new_empty((1, T, H, V)), q.new_empty((N, H, K, V) if output_final_state else (0,), dtype=torch.float32)
 
 
+torch.library.register_autograd("gdkvm::gdr_lkva_varlen", _no_backward("gdr_lkva_varlen"))
+
 torch.library.define("gdkvm::l2norm", "(Tensor x, float eps=1e-6) -> Tensor")
 
 
@@ -287,7 +437,16 @@ def gdr_lkva(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, g: torch.Tensor,
     q,k [B,T,H,K]; v [B,T,H,V]; g (log-space gate) and beta [B,T,H]; initial_state fp32 [B,H,K,V].
     Returns ``(o [B,T,H,V] in q.dtype, final_state fp32 [B,H,K,V] or None)``.
     ``frame_tokens=C`` declares T = F*C with every frame one chunk (north_star).
+    Differentiable (bf16, d_k = 64, d_v in {128, 256}): when gradients are enabled and an input requires them, the call
+    runs the training forward and autograd runs the hand-written backward kernel (csrc/gdr_bwd_sm100.cu).
     """
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (q, k, v, g, beta, initial_state)):
+        # a call that will be differentiated: the training forward (keeps the chunk-start states for the backward kernel)
+        why = train_unsupported_reason(q, k, v)
+        if why:
+            raise NotImplementedError(f"gdkvm_b200.gdr_lkva cannot be differentiated for these tensors: {why}")
+        o, sT, _ = torch.ops.gdkvm.gdr_lkva_train(q, k, v, g, beta, scale, initial_state, flags)
+        return o, (sT if output_final_state else None)
     o, sT = torch.ops.gdkvm.gdr_lkva(q, k, v, g, beta, scale, initial_state, output_final_state,
                                      frame_tokens, flags)
     return o, (sT if output_final_state else None)

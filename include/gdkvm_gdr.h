@@ -165,6 +165,60 @@ int gdkvm_gdr_plan_segments(const GdkvmGdrParams* params, int sm_count);
 int gdkvm_l2norm_fwd(const void* x, void* y, int64_t rows, int32_t D, int64_t x_row_stride, int64_t y_row_stride,
                      int32_t dtype, float eps, void* cuda_stream);
 
+/*
+ * ---- training: forward that keeps what the backward pass needs, and the backward pass ----
+ *   replaces: the autograd formula of the reference memory module (the upstream model is trained: reference
+ *   website/src/pages/[lang]/reprod/index.astro:238-252; shape of the work: fla/ops/gated_delta_rule/chunk.py:117).
+ *
+ * gdkvm_gdr_fwd_train = gdkvm_gdr_fwd on the tcgen05 chunk kernel (bf16 I/O, K = 64, V in {128, 256}; anything else returns
+ * GDKVM_ERR_UNSUPPORTED -- there is no slow training path) which ALSO writes the bf16 state at the start of every 64-token
+ * chunk into `chunk_states`, a caller-owned device buffer of gdkvm_gdr_chunk_states_bytes(B, T, H, K, V) bytes laid out
+ * [B*H][ceil(T/64)][V][K].  The token stream is tiled flat in 64-token chunks (frame_tokens is ignored; results equal
+ * within the op's tolerance).
+ */
+int gdkvm_gdr_fwd_train(const GdkvmGdrParams* params, void* chunk_states, void* cuda_stream);
+int64_t gdkvm_gdr_chunk_states_bytes(int32_t B, int32_t T, int32_t H, int32_t K, int32_t V);
+
+/*
+ * Gradients of (readout, final_state) with respect to (q, k, v, g, beta, initial_state), given the cotangents d_o [B,T,H,V]
+ * (io dtype) and d_final_state [B,H,K,V] (fp32, may be NULL = zero).  dq, dk, dv: io dtype, strides in elements, innermost
+ * dimension contiguous; dg, dbeta: fp32, CONTIGUOUS [B,T,H]; d_initial_state: fp32 [B,H,K,V], may be NULL (not written).
+ * One kernel: per (clip, head) chain a reverse-time scan over 64-token chunks with the state cotangent in registers.
+ */
+typedef struct GdkvmGdrBwdParams {
+    uint32_t struct_size;        /* = sizeof(GdkvmGdrBwdParams)                                */
+    uint32_t flags;              /* reserved, 0                                                */
+    const void* q;
+    const void* k;
+    const void* v;
+    const void* g;
+    const void* beta;
+    const void* d_o;             /* cotangent of the readout                                   */
+    const float* d_final_state;  /* cotangent of the final state, may be NULL                  */
+    const void* chunk_states;    /* written by gdkvm_gdr_fwd_train on the same inputs          */
+    void* dq;
+    void* dk;
+    void* dv;
+    float* dg;
+    float* dbeta;
+    float* d_initial_state;      /* may be NULL                                                */
+    int64_t q_stride[3];
+    int64_t k_stride[3];
+    int64_t v_stride[3];
+    int64_t do_stride[3];
+    int64_t g_stride[3];
+    int64_t beta_stride[3];
+    int64_t dq_stride[3];
+    int64_t dk_stride[3];
+    int64_t dv_stride[3];
+    int32_t B, T, H, K, V;
+    int32_t io_dtype;
+    int32_t gate_dtype;
+    float scale;
+} GdkvmGdrBwdParams;
+
+int gdkvm_gdr_bwd(const GdkvmGdrBwdParams* params, void* cuda_stream);
+
 /* Number of kernels this library has launched in the calling process (bench "gpu_launches"). */
 uint64_t gdkvm_launch_count(void);
 

@@ -143,7 +143,7 @@ def gdr_chunk_ref(
 
 def gdr_backward_ref(q, k, v, g, beta, do, dsT=None, scale=None, initial_state=None, dtype=torch.float64):
     """Gradients of the token recurrence by reverse-mode differentiation of the same four lines (ground truth for the
-    backward pass, SURVEY.md section 8f rank 1 -- not built yet; this is the checker it will be held to).
+    backward pass, SURVEY.md section 8f rank 1: the checker ``csrc/gdr_bwd_sm100.cu`` is held to).
 
     ``do`` [B,T,H,V] and ``dsT`` [B,H,K,V] (optional) are the cotangents of the readout and of the final state.  Returns
     ``(dq, dk, dv, dg, dbeta, dS0)`` in ``dtype`` (float64 by default: the recurrence is re-run in that precision).
@@ -167,6 +167,78 @@ def gdr_backward_ref(q, k, v, g, beta, do, dsT=None, scale=None, initial_state=N
     if dsT is not None:
         loss = loss + (S * dsT.detach().to("cpu", dtype)).sum()
     return torch.autograd.grad(loss, (q_, k_, v_, g_, b_, S0))
+
+
+def gdr_chunk_backward_ref(q, k, v, g, beta, do, dsT=None, scale=None, S0=None, C=64, dt=torch.float64):
+    """Chunked (WY/UT) restatement of the backward pass -- the algebra ``csrc/gdr_bwd_sm100.cu`` executes, chunk by chunk in
+    reverse time with the state cotangent ``dS`` carried across chunks; checked against ``gdr_backward_ref`` (autograd
+    through the token recurrence) in tests/test_oracle.py.  Flat ``C``-token chunks.  Returns (dq, dk, dv, dg, dbeta, dS0)."""
+    B, T, H, K = k.shape; V = v.shape[-1]
+    scale = scale or 1 / math.sqrt(K)
+    f = lambda x: x.to(dt).permute(0, 2, 1, 3) if x.dim() == 4 else x.to(dt).permute(0, 2, 1)
+    q, k, v, do = map(f, (q, k, v, do)); g, beta = f(g), f(beta)
+    S = torch.zeros(B, H, K, V, dtype=dt) if S0 is None else S0.to(dt).clone()
+    sched = chunk_schedule(T, 0, C)
+    # forward: store chunk-start states and Vn
+    Ss, Vns = [], []
+    for (t0, n) in sched:
+        sl = slice(t0, t0+n)
+        Q, Kc, Vc = q[:, :, sl], k[:, :, sl], v[:, :, sl]
+        G = g[:, :, sl].cumsum(-1); bt = beta[:, :, sl]; e = G.exp()
+        low = torch.tril(torch.ones(n, n, dtype=torch.bool))
+        D = torch.where(low, G[..., :, None] - G[..., None, :], torch.full((n, n), -float('inf'), dtype=dt)).exp()
+        A = torch.tril(bt[..., None] * (Kc @ Kc.transpose(-1, -2)) * D, -1)
+        eye = torch.eye(n, dtype=dt).expand_as(A)
+        Tm = torch.linalg.solve_triangular(eye + A, eye.clone(), upper=False)
+        W = Tm @ (bt[..., None] * e[..., None] * Kc); U = Tm @ (bt[..., None] * Vc)
+        Vn = U - W @ S
+        Ss.append(S); Vns.append(Vn)
+        S = e[..., -1:, None] * S + (Kc * (e[..., -1:] / e)[..., None]).transpose(-1, -2) @ Vn
+    dS = torch.zeros_like(S) if dsT is None else dsT.to(dt).clone()
+    dq = torch.zeros_like(q); dk = torch.zeros_like(k); dv = torch.zeros_like(v); dg = torch.zeros_like(g); db = torch.zeros_like(beta)
+    for ci in range(len(sched) - 1, -1, -1):
+        t0, n = sched[ci]; sl = slice(t0, t0+n)
+        Q, Kc, Vc, dO = q[:, :, sl], k[:, :, sl], v[:, :, sl], do[:, :, sl]
+        S, Vn = Ss[ci], Vns[ci]
+        G = g[:, :, sl].cumsum(-1); bt = beta[:, :, sl]; e = G.exp(); gam = e[..., -1]
+        low = torch.tril(torch.ones(n, n, dtype=torch.bool))
+        D = torch.where(low, G[..., :, None] - G[..., None, :], torch.full((n, n), -float('inf'), dtype=dt)).exp()
+        KK = Kc @ Kc.transpose(-1, -2)
+        A = torch.tril(bt[..., None] * KK * D, -1)
+        eye = torch.eye(n, dtype=dt).expand_as(A)
+        Tm = torch.linalg.solve_triangular(eye + A, eye.clone(), upper=False)
+        Bt = (bt * e)[..., None] * Kc; Vt = bt[..., None] * Vc
+        W = Tm @ Bt
+        P = (Q @ Kc.transpose(-1, -2)) * D           # tril via D
+        Kh = (gam[..., None] / e)[..., None] * Kc
+        dVn = scale * P.transpose(-1, -2) @ dO + Kh @ dS
+        dSn = gam[..., None, None] * dS + scale * (e[..., None] * Q).transpose(-1, -2) @ dO - W.transpose(-1, -2) @ dVn
+        dP = scale * (dO @ Vn.transpose(-1, -2)) * low
+        dQS = scale * dO @ S.transpose(-1, -2)        # C x K
+        dPD = dP * D
+        dQ = e[..., None] * dQS + dPD @ Kc
+        dK = dPD.transpose(-1, -2) @ Q
+        dKh = Vn @ dS.transpose(-1, -2)
+        dK = dK + (gam[..., None] / e)[..., None] * dKh
+        dW = -dVn @ S.transpose(-1, -2)
+        dT = dW @ Bt.transpose(-1, -2) + dVn @ Vt.transpose(-1, -2)
+        dBt = Tm.transpose(-1, -2) @ dW; dVt = Tm.transpose(-1, -2) @ dVn
+        dV = bt[..., None] * dVt
+        dK = dK + (bt * e)[..., None] * dBt
+        dbeta = e * (dBt * Kc).sum(-1) + (dVt * Vc).sum(-1)
+        dA = -(Tm.transpose(-1, -2) @ dT @ Tm.transpose(-1, -2)) * torch.tril(torch.ones(n, n, dtype=dt), -1)
+        dbeta = dbeta + (dA * KK * D).sum(-1)
+        M = dA * bt[..., None] * D
+        dK = dK + M @ Kc + M.transpose(-1, -2) @ Kc
+        dGam = e * (Q * dQS).sum(-1) + (dP * P).sum(-1) - (dP * P).sum(-2) + (dA * A).sum(-1) - (dA * A).sum(-2) \
+               + (dBt * Bt).sum(-1) - (dKh * Kh).sum(-1)
+        last = (dKh * Kh).sum((-1, -2)) + gam * (dS * S).sum((-1, -2))
+        dGam[..., -1] += last
+        dg[:, :, sl] = dGam.flip(-1).cumsum(-1).flip(-1)
+        dq[:, :, sl] = dQ; dk[:, :, sl] = dK; dv[:, :, sl] = dV; db[:, :, sl] = dbeta
+        dS = dSn
+    p = lambda x: x.permute(0, 2, 1, 3) if x.dim() == 4 else x.permute(0, 2, 1)
+    return p(dq), p(dk), p(dv), p(dg), p(db), dS
 
 
 def gdr_recurrent_varlen_ref(q, k, v, g, beta, cu_seqlens, scale=None, initial_state=None):

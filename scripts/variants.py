@@ -15,10 +15,14 @@ if sys.argv[1] == "build":
     print("built", [n for n, _ in procs]); sys.exit(0)
 for name in sys.argv[2:]:
     env = dict(os.environ, GDKVM_LIB=lib(name))
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "10", "--warmup", "3", "--no-e2e", "--no-cpu"],
-                         capture_output=True, text=True, env=env)
+    if name == "default":
+        env.pop("GDKVM_LIB")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "5", "--no-e2e", "--no-cpu", "--no-extras",
+                          "--sustained-seconds", os.environ.get("SUSTAINED", "2.5")], capture_output=True, text=True, env=env)
     try:
-        ms = json.loads(out.stdout.strip().splitlines()[-1])["ms_per_step"]
-        print(f"{name:24s} {ms:7.4f} ms/step", flush=True)
+        b = json.loads(out.stdout.strip().splitlines()[-1])
+        su = b.get("sustained") or {}
+        print(f"{name:24s} burst {b['ms_per_step']:7.4f} ms/step   sustained {su.get('ms_per_step', float('nan')):7.4f} "
+              f"(last quarter {su.get('last_quarter_ms_per_step', float('nan')):7.4f}) clocks {su.get('clocks')}", flush=True)
     except Exception:
         print(f"{name:24s} FAILED {out.stderr[-300:]}", flush=True)

@@ -1,0 +1,160 @@
+"""GPU tests of the backward pass: csrc/gdr_bwd_sm100.cu through torch autograd and through
+the C ABI, against reverse-mode differentiation of the token recurrence in float64 (oracle.gdr_ref.gdr_backward_ref) on
+the same bf16-rounded inputs.  Tolerance: max|a-b| / max|b| <= 2e-2 per gradient tensor (north_star's bf16 I/O bound)."""
+import pytest
+import torch
+
+from oracle.gdr_ref import gdr_backward_ref, gdr_recurrent_ref, make_inputs, max_rel_err, rms_rel_err
+
+pytestmark = pytest.mark.gpu
+NAMES = ("dq", "dk", "dv", "dg", "dbeta", "dS0")
+CHUNKED, FLAT = 0x2, 0x4
+
+
+@pytest.fixture(scope="module")
+def op(built_lib):
+    assert torch.cuda.is_available(), "-m gpu tests need a B200"
+    import gdkvm_b200
+    return gdkvm_b200
+
+
+def _case(B, T, H, V, seed, C=0, corr=False, with_s0=True, with_dsT=True):
+    q, k, v, g, beta, S0 = make_inputs(B, T, H, 64, V, seed=seed, frame_tokens=C, correlated=corr, dtype=torch.bfloat16)
+    gen = torch.Generator().manual_seed(seed + 1000)
+    do = torch.randn(B, T, H, V, generator=gen).bfloat16()
+    dsT = torch.randn(B, H, 64, V, generator=gen) if with_dsT else None
+    return q, k, v, g, beta, (S0 if with_s0 else None), do, dsT
+
+
+def _grads_on_device(op, q, k, v, g, beta, S0, do, dsT):
+    leaf = lambda x: x.cuda().requires_grad_(True) if x is not None else None
+    qd, kd, vd, gd, bd, sd = map(leaf, (q, k, v, g, beta, S0))
+    o, sT = op.gdr_lkva(qd, kd, vd, gd, bd, None, sd, True)
+    assert o.requires_grad and sT.requires_grad
+    loss = (o.float() * do.cuda().float()).sum()
+    if dsT is not None:
+        loss = loss + (sT * dsT.cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    return [x.grad.float().cpu() if x is not None else None for x in (qd, kd, vd, gd, bd, sd)], o.detach(), sT.detach()
+
+
+@pytest.mark.parametrize("case", [
+    # B, T, H, V, frame_tokens, correlated, with S0, with dsT
+    (1, 64, 1, 128, 0, False, True, True),              # one full chunk, one value half
+    (2, 3 * 64 + 10, 2, 256, 0, False, True, True),     # ragged tail, two value halves
+    (2, 5 * 49, 3, 256, 49, True, True, False),         # EchoNet-shaped frames, correlated keys, no final-state cotangent
+    (1, 37, 2, 128, 0, False, False, True),             # less than a chunk, zero initial state
+    (1, 8 * 64, 2, 256, 0, False, True, True),          # eight chunks: the state cotangent carried a long way
+])
+def test_backward_vs_float64_autograd(op, case):
+    B, T, H, V, C, corr, w_s0, w_dsT = case
+    q, k, v, g, beta, S0, do, dsT = _case(B, T, H, V, 200 + T, C, corr, w_s0, w_dsT)
+    ref = gdr_backward_ref(q, k, v, g, beta, do, dsT, None, S0)
+    got, o, sT = _grads_on_device(op, q, k, v, g, beta, S0, do, dsT)
+    o_ref, s_ref = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+    assert max_rel_err(o, o_ref) <= 2e-2 and max_rel_err(sT, s_ref) <= 2e-2          # the training forward itself
+    for name, a, b in zip(NAMES, got, ref):
+        if a is None:
+            continue
+        e, r = max_rel_err(a, b.float()), rms_rel_err(a, b.float())
+        print(f"{case}: {name} max-rel {e:.2e} rms-rel {r:.2e}")
+        assert e <= 2e-2 and r <= 1e-2, (name, e, r)
+
+
+def test_training_forward_is_the_inference_forward(op):
+    """gdr_lkva_train = the tcgen05 kernel on flat 64-token chunks, bit for bit, plus the bf16 chunk-start states."""
+    q, k, v, g, beta, S0, _, _ = _case(3, 5 * 64 + 7, 2, 256, 301)
+    qd, kd, vd, gd, bd, sd = (x.cuda() for x in (q, k, v, g, beta, S0))
+    o, sT = op.gdr_lkva(qd, kd, vd, gd, bd, None, sd, True, 0, CHUNKED | FLAT)
+    o2, sT2, cs = torch.ops.gdkvm.gdr_lkva_train(qd, kd, vd, gd, bd, None, sd, 0)
+    assert torch.equal(o, o2) and torch.equal(sT, sT2)
+    assert cs.shape == (3 * 2, 6, 256, 64)
+    assert torch.equal(cs[:, 0].float(), sd.reshape(6, 64, 256).transpose(1, 2).bfloat16().float())      # chunk 0 starts at S0
+    # chunk c starts where a call over the first 64 c tokens ends
+    _, s3 = op.gdr_lkva(qd[:, :192], kd[:, :192], vd[:, :192], gd[:, :192], bd[:, :192], None, sd, True, 0, CHUNKED | FLAT)
+    assert max_rel_err(cs[:, 3].float(), s3.reshape(6, 64, 256).transpose(1, 2)) <= 1e-2
+
+
+def test_module_and_alias_are_differentiable(op):
+    q, k, v, g, beta, S0, do, dsT = _case(2, 130, 2, 128, 302)
+    leaf = lambda x: x.cuda().requires_grad_(True)
+    qd, kd, vd, gd, bd, sd = map(leaf, (q, k, v, g, beta, S0))
+    mem = op.GDRMemory(frame_tokens=0)
+    o, sT = mem(qd, kd, vd, gd, bd, sd)
+    ((o.float() * do.cuda().float()).sum() + (sT * dsT.cuda()).sum()).backward()
+    g1 = [x.grad.clone() for x in (qd, kd, vd, gd, bd, sd)]
+    for x in (qd, kd, vd, gd, bd, sd):
+        x.grad = None
+    o2, sT2 = op.chunk_gated_delta_rule(qd, kd, vd, gd, bd, initial_state=sd, output_final_state=True)
+    ((o2.float() * do.cuda().float()).sum() + (sT2 * dsT.cuda()).sum()).backward()
+    for a, x, n in zip(g1, (qd, kd, vd, gd, bd, sd), NAMES):
+        tol = 0 if n in ("dq", "dk", "dv", "dS0") else 1e-4          # dg / dbeta are summed with shared-memory atomics
+        assert max_rel_err(x.grad.float(), a.float()) <= tol, n
+    # only some inputs need gradients; no_grad runs the plain forward
+    o3, _ = op.gdr_lkva(qd.detach(), kd.detach(), vd.detach().requires_grad_(True), gd.detach(), bd.detach(), None, None, False)
+    o3.float().sum().backward()
+    with torch.no_grad():
+        o4, _ = op.gdr_lkva(qd, kd, vd, gd, bd, None, sd, True)
+    assert not o4.requires_grad
+
+
+def test_what_cannot_be_differentiated_says_so(op):
+    q, k, v, g, beta, S0 = make_inputs(1, 40, 1, 64, 128, seed=5)                 # fp32 I/O
+    qd = q.cuda().requires_grad_(True)
+    with pytest.raises(NotImplementedError, match="bf16"):
+        op.gdr_lkva(qd, k.cuda(), v.cuda(), g.cuda(), beta.cuda())
+    qb, kb, vb = (x.cuda().bfloat16() for x in (q, k, v))
+    o, _ = torch.ops.gdkvm.gdr_lkva(qb.requires_grad_(True), kb, vb, g.cuda(), beta.cuda())          # the raw inference op
+    with pytest.raises(NotImplementedError, match="no backward formula"):
+        o.float().sum().backward()
+    cu = torch.tensor([0, 40], dtype=torch.int32, device="cuda")
+    o, _ = op.gdr_lkva_varlen(qb, kb, vb, g.cuda(), beta.cuda(), cu)
+    with pytest.raises(NotImplementedError, match="forward-only"):
+        o.float().sum().backward()
+    with pytest.raises(NotImplementedError):                                                         # d_v = 64
+        op.gdr_lkva(qb, kb, vb[..., :64].contiguous().requires_grad_(True), g.cuda(), beta.cuda())
+
+
+def test_l2norm_is_differentiable(op):
+    x = torch.randn(3, 17, 2, 64, generator=torch.Generator().manual_seed(7))
+    xd = x.cuda().requires_grad_(True)
+    w = torch.randn_like(x).cuda()
+    (op.l2norm(xd) * w).sum().backward()
+    xr = x.double().requires_grad_(True)
+    ((xr * torch.rsqrt(xr.square().sum(-1, keepdim=True) + 1e-6)) * w.cpu().double()).sum().backward()
+    assert max_rel_err(xd.grad, xr.grad.float()) <= 1e-5
+
+
+def test_full_size_backward_linearity(op):
+    """BASELINE configs[1] through forward + backward: gradients are linear in the cotangents, and doubling is exact in
+    binary floating point -- a size-independent check of every chain (dg / dbeta up to the order of their atomics)."""
+    g0 = torch.Generator(device="cuda").manual_seed(77)
+    B, T, H, K, V = 64, 128 * 49, 8, 64, 256
+    rn = lambda *s: torch.randn(*s, generator=g0, device="cuda", dtype=torch.float32)
+    l2 = lambda x: torch.nn.functional.normalize(x, dim=-1)
+    q, k, v = l2(rn(B, T, H, K)).bfloat16(), l2(rn(B, T, H, K)).bfloat16(), rn(B, T, H, V).bfloat16()
+    beta, g = torch.sigmoid(rn(B, T, H)), torch.nn.functional.logsigmoid(rn(B, T, H) + 4.0)
+    S0, do, dsT = 0.1 * rn(B, H, K, V), rn(B, T, H, V).bfloat16(), rn(B, H, K, V)
+    o, sT, cs = torch.ops.gdkvm.gdr_lkva_train(q, k, v, g, beta, None, S0, 0)
+    sc = 1.0 / 8.0
+    a = torch.ops.gdkvm.gdr_lkva_bwd(q, k, v, g, beta, cs, do, dsT, sc, True)
+    b = torch.ops.gdkvm.gdr_lkva_bwd(q, k, v, g, beta, cs, do * 2, dsT * 2, sc, True)
+    torch.cuda.synchronize()
+    for n, x, y in zip(NAMES, a, b):
+        assert bool(torch.isfinite(x.float()).all()), n
+        if n in ("dg", "dbeta"):
+            assert max_rel_err(y, x * 2) <= 1e-4, n
+        else:
+            assert torch.equal(y.float(), x.float() * 2), n
+    # two clips against the float64 oracle would take minutes at this length; one chain, first 6 frames of clip 0 instead
+    sl, tt = slice(0, 1), 6 * 49
+    ref = gdr_backward_ref(q[sl, :tt, :1].cpu(), k[sl, :tt, :1].cpu(), v[sl, :tt, :1].cpu(), g[sl, :tt, :1].cpu(), beta[sl, :tt, :1].cpu(),
+                           do[sl, :tt, :1].cpu(), None, None, S0[sl, :1].cpu())
+    leaf = lambda x: x.clone().requires_grad_(True)
+    qs, ks, vs = leaf(q[sl, :tt, :1].contiguous()), leaf(k[sl, :tt, :1].contiguous()), leaf(v[sl, :tt, :1].contiguous())
+    gs, bs, ss = leaf(g[sl, :tt, :1].contiguous()), leaf(beta[sl, :tt, :1].contiguous()), leaf(S0[sl, :1].contiguous())
+    o1, _ = op.gdr_lkva(qs, ks, vs, gs, bs, None, ss, True)
+    (o1.float() * do[sl, :tt, :1].float()).sum().backward()
+    for n, x, r in zip(NAMES, (qs, ks, vs, gs, bs, ss), ref):
+        assert max_rel_err(x.grad.float(), r.float()) <= 2e-2, n
