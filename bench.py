@@ -323,6 +323,101 @@ def run_extras(args, dev, sampler, main_inputs, main_ms):
                  wall_s=time.time() - t0)
         return d
 
+    def backward():
+        B, H, K, V, C = W1["clips"], W1["heads"], W1["d_k"], W1["d_v"], W1["frame_tokens"]
+        T = W1["frames"] * C
+        gen = torch.Generator(device=dev).manual_seed(99)
+        d_o = torch.randn(B, T, H, V, generator=gen, device=dev, dtype=torch.float32).bfloat16()
+        d_sT = torch.randn(B, H, K, V, generator=gen, device=dev, dtype=torch.float32)
+        sc = 1.0 / K ** 0.5
+        _, _, cs = torch.ops.gdkvm.gdr_lkva_train(q, k, v, g, beta, None, S0, 0)
+        fwd = lambda: torch.ops.gdkvm.gdr_lkva_train(q, k, v, g, beta, None, S0, 0)
+        bwd = lambda: torch.ops.gdkvm.gdr_lkva_bwd(q, k, v, g, beta, cs, d_o, d_sT, sc, True)
+        ms_f, st_f, win_f = time_for(fwd, args.extra_seconds / 2)
+        ms_b, st_b, win_b = time_for(bwd, args.extra_seconds)
+        NC = (T + 63) // 64
+        cs_bytes = B * H * NC * V * K * 2
+        # backward: q,k,v,do read + dq,dk,dv written + g,beta read + dg,dbeta written per token-head; chunk states read; dS in/out
+        ab_b = B * T * H * ((2 * K + 2 * V) * 2 + (2 * K + V) * 2 + 16) + cs_bytes + B * H * 2 * K * V * 4
+        ab_f = algorithmic_bytes(B, T, H, K, V) + cs_bytes
+        out = extra_line(B, T, H, K, V, W1["frames"], ms_b, st_b, win_b, sampler,
+                         "backward kernel alone on configs[1] (gdr_bwd_kernel: reverse-time chunk scan, mma.sync); dq, dk, dv, dg, dbeta, dS0 "
+                         "from d_o and d_final_state", ab_b)
+        out["training_forward"] = extra_line(B, T, H, K, V, W1["frames"], ms_f, st_f, win_f, sampler,
+                                             "gdr_chunk_kernel + bf16 chunk-start states written for the backward pass", ab_f)
+        out["forward_plus_backward_ms"] = ms_f + ms_b
+        return out
+
+    def prologue():
+        # features [B, T, 256] -> q | k | v | g | beta -> memory op, configs[1] geometry: fused tcgen05 projection kernel against
+        # the library route (cuBLAS linear -> y in HBM -> split / normalise / activations in torch), each followed by the op
+        B, H, K, V, C = W1["clips"], W1["heads"], W1["d_k"], W1["d_v"], W1["frame_tokens"]
+        T, D = W1["frames"] * C, 256
+        N = H * (2 * K + V) + 2 * H
+        gen = torch.Generator(device=dev).manual_seed(55)
+        x = torch.randn(B, T, D, generator=gen, device=dev, dtype=torch.float32).bfloat16()
+        w = (torch.randn(N, D, generator=gen, device=dev, dtype=torch.float32) / D ** 0.5).bfloat16()
+        o2 = torch.empty(B, T, H, V, dtype=torch.bfloat16, device=dev)
+        sT2 = torch.empty(B, H, K, V, dtype=torch.float32, device=dev)
+
+        def fused():
+            qq, kk, vv, gg, bb = gdkvm_b200.qkvgb_project(x, w, None, H, K, V)
+            gdkvm_b200.gdr_lkva_out(qq, kk, vv, gg, bb, o2, sT2, None, S0, C, 0)
+
+        def unfused():
+            with torch.no_grad():
+                qq, kk, vv, gg, bb = gdkvm_b200.qkvgb_project_reference(x, w, None, H, K, V)
+            gdkvm_b200.gdr_lkva_out(qq, kk, vv, gg, bb, o2, sT2, None, S0, C, 0)
+
+        def norm_then_op():
+            gdkvm_b200.gdr_lkva_out(gdkvm_b200.l2norm(q), gdkvm_b200.l2norm(k), v, g, beta, o2, sT2, None, S0, C, 0)
+
+        ms_p, _, _ = time_for(lambda: gdkvm_b200.qkvgb_project(x, w, None, H, K, V), args.extra_seconds / 2)
+        ms_f, st_f, win_f = time_for(fused, args.extra_seconds)
+        ms_u, _, _ = time_for(unfused, args.extra_seconds / 2)
+        ms_n, _, _ = time_for(norm_then_op, args.extra_seconds / 2)
+        R = B * T
+        ab_p = R * D * 2 + N * D * 2 + R * H * ((2 * K + V) * 2 + 8)          # features + weight read, op operands written
+        peak, _ = measured_peak_gbs()
+        tf = 2.0 * R * N * D / (ms_p * 1e-3) / 1e12
+        return {"ms_per_step": ms_f, "steps": st_f, "value": B * W1["frames"] / (ms_f * 1e-3), "unit": UNIT,
+                "projection_kernel_ms": ms_p, "projection_roofline": {"bound": "hbm", "achieved": ab_p / (ms_p * 1e-3) / 1e9, "peak": peak,
+                                                                      "unit": "GB/s", "frac": ab_p / (ms_p * 1e-3) / 1e9 / peak,
+                                                                      "algorithmic_bytes_per_step": ab_p, "TFLOPs": tf},
+                "unfused_library_route_ms": ms_u, "speedup_over_unfused": ms_u / ms_f, "l2norm_x2_plus_op_ms": ms_n,
+                "clocks": sampler.window(*win_f) if sampler is not None else None,
+                "note": "features [64, 6272, 256] bf16 -> q,k,v,g,beta (N = 3088 columns) -> op. fused = qkvgb_proj_kernel (tcgen05 GEMM, "
+                        "L2-norm / sigmoid / logsigmoid epilogue) + op; unfused = torch linear (cuBLAS) + split + normalise + activations + op; "
+                        "l2norm_x2_plus_op = the round-1 prologue (two normalisation passes over given q, k, no GEMM)"}
+
+    def full_forward():
+        # BASELINE configs[4]: encoder + KPFF + projection + memory + decoder (random init, bf16, EchoNet shape), frames/s end to
+        # end, and the share of it that is this package's memory path
+        from gdkvm_b200.model import GDKVMSkeleton
+        torch.manual_seed(0)
+        model = GDKVMSkeleton().to(dev).to(torch.bfloat16).eval()
+        Bc, Fr = 8, W1["frames"]
+        clip = torch.randn(Bc, Fr, 1, 112, 112, device=dev, dtype=torch.bfloat16)
+        with torch.no_grad():
+            fn = lambda: model(clip)
+            ms, steps, win = time_for(fn, args.extra_seconds, warmup=2, min_steps=2)
+            # the memory path alone on the same token count: projection kernel + op
+            tok = torch.randn(Bc, Fr * 49, 256, device=dev, dtype=torch.bfloat16)
+            wq, bq = model.proj_weight.to(torch.bfloat16), model.proj_bias.float()
+
+            def mem():
+                qq, kk, vv, gg, bb = gdkvm_b200.qkvgb_project(tok, wq, bq, 8, 64, 256)
+                gdkvm_b200.gdr_lkva(qq, kk, vv, gg, bb, None, None, True, 49)
+            ms_m, _, _ = time_for(mem, args.extra_seconds / 2)
+        return {"ms_per_step": ms, "steps": steps, "value": Bc * Fr / (ms * 1e-3), "unit": "frames/s (end to end)",
+                "clips": Bc, "frames": Fr, "memory_path_ms": ms_m, "memory_path_share": ms_m / ms,
+                "clocks": sampler.window(*win) if sampler is not None else None,
+                "note": "BASELINE configs[4] skeleton: random-init stand-in encoder / KPFF / decoder in plain PyTorch (cuDNN), bf16, 8 clips x "
+                        "128 frames x 112x112; memory path = fused projection kernel + tcgen05 memory op (this package)"}
+
+    guarded("backward", backward)
+    guarded("full_forward", full_forward)
+    guarded("prologue_plus_op", prologue)
     guarded("varlen_0.5", varlen)
     guarded("camus", camus)
     guarded("long_clip", long_clip)

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 # GDKVM_LIB: load another build of the same ABI (profiling / ablation builds made by scripts/)
 LIB_PATH = os.environ.get("GDKVM_LIB") or os.path.join(PKG_DIR, "libgdkvm_gdr.so")
-SOURCES = ["gdr_api.cu", "gdr_recurrent.cu", "gdr_chunked_sm100.cu", "gdr_bwd_sm100.cu", "l2norm.cu"]
+SOURCES = ["gdr_api.cu", "gdr_recurrent.cu", "gdr_chunked_sm100.cu", "gdr_bwd_sm100.cu", "gdr_proj_sm100.cu", "l2norm.cu"]
 
 
 def _nvcc() -> str:

@@ -21,6 +21,8 @@ EXPORTED_SYMBOLS = (
     "gdkvm_abi_version", "gdkvm_strerror", "gdkvm_last_cuda_error",
     "gdkvm_gdr_fwd", "gdkvm_gdr_fwd_varlen", "gdkvm_gdr_plan", "gdkvm_gdr_plan_segments", "gdkvm_gdr_plan_reason",
     "gdkvm_launch_count", "gdkvm_l2norm_fwd", "gdkvm_gdr_fwd_train", "gdkvm_gdr_chunk_states_bytes", "gdkvm_gdr_bwd",
+    "gdkvm_gdr_fwd_train_varlen", "gdkvm_gdr_chunk_states_bytes_varlen",
+    "gdkvm_qkvgb_project_fwd",
 )
 
 
@@ -52,6 +54,18 @@ class GdkvmGdrBwdParams(ctypes.Structure):
         ("dq_stride", ctypes.c_int64 * 3), ("dk_stride", ctypes.c_int64 * 3), ("dv_stride", ctypes.c_int64 * 3),
         ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("H", ctypes.c_int32), ("K", ctypes.c_int32), ("V", ctypes.c_int32),
         ("io_dtype", ctypes.c_int32), ("gate_dtype", ctypes.c_int32), ("scale", ctypes.c_float),
+        ("cu_seqlens", ctypes.c_void_p), ("cu_seqlens_bytes", ctypes.c_int32), ("n_seqs", ctypes.c_int32),
+    ]
+
+
+class GdkvmProjParams(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32), ("flags", ctypes.c_uint32),
+        ("x", ctypes.c_void_p), ("w", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+        ("q", ctypes.c_void_p), ("k", ctypes.c_void_p), ("v", ctypes.c_void_p), ("g", ctypes.c_void_p), ("beta", ctypes.c_void_p),
+        ("R", ctypes.c_int64), ("x_row_stride", ctypes.c_int64),
+        ("D", ctypes.c_int32), ("H", ctypes.c_int32), ("K", ctypes.c_int32), ("V", ctypes.c_int32),
+        ("eps", ctypes.c_float), ("reserved", ctypes.c_int32),
     ]
 
 
@@ -92,8 +106,15 @@ def load() -> ctypes.CDLL:
             lib.gdkvm_gdr_fwd_train.argtypes = [ctypes.POINTER(GdkvmGdrParams), ctypes.c_void_p, ctypes.c_void_p]
             lib.gdkvm_gdr_chunk_states_bytes.restype = ctypes.c_int64
             lib.gdkvm_gdr_chunk_states_bytes.argtypes = [ctypes.c_int32] * 5
+            lib.gdkvm_gdr_fwd_train_varlen.restype = ctypes.c_int
+            lib.gdkvm_gdr_fwd_train_varlen.argtypes = [ctypes.POINTER(GdkvmGdrParams), ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
+                                                       ctypes.c_void_p, ctypes.c_void_p]
+            lib.gdkvm_gdr_chunk_states_bytes_varlen.restype = ctypes.c_int64
+            lib.gdkvm_gdr_chunk_states_bytes_varlen.argtypes = [ctypes.c_int32] * 5
             lib.gdkvm_gdr_bwd.restype = ctypes.c_int
             lib.gdkvm_gdr_bwd.argtypes = [ctypes.POINTER(GdkvmGdrBwdParams), ctypes.c_void_p]
+            lib.gdkvm_qkvgb_project_fwd.restype = ctypes.c_int
+            lib.gdkvm_qkvgb_project_fwd.argtypes = [ctypes.POINTER(GdkvmProjParams), ctypes.c_void_p]
             if lib.gdkvm_abi_version() != GDKVM_ABI_VERSION:
                 raise RuntimeError("libgdkvm_gdr.so ABI version mismatch; rebuild")
             _lib = lib

@@ -185,6 +185,31 @@ int gdkvm_gdr_fwd_train(const GdkvmGdrParams* params, void* chunk_states, void* 
     return GDKVM_OK;
 }
 
+int64_t gdkvm_gdr_chunk_states_bytes_varlen(int32_t T, int32_t n_seqs, int32_t H, int32_t K, int32_t V) {
+    if (T < 0 || n_seqs <= 0 || H <= 0 || K <= 0 || V <= 0) return 0;
+    return ((int64_t)T / 64 + n_seqs + 1) * H * V * K * 2;
+}
+
+int gdkvm_gdr_fwd_train_varlen(const GdkvmGdrParams* params, const void* cu_seqlens, int32_t cu_seqlens_bytes, int32_t n_seqs,
+                               void* chunk_states, void* cuda_stream) {
+    int rc = gdkvm::validate(params);
+    if (rc != GDKVM_OK) return rc;
+    if (params->B != 1 || n_seqs < 1 || (cu_seqlens_bytes != 4 && cu_seqlens_bytes != 8)) return GDKVM_ERR_SHAPE;
+    if (cu_seqlens == nullptr || chunk_states == nullptr) return GDKVM_ERR_NULL;
+    if (reinterpret_cast<uintptr_t>(cu_seqlens) % (uintptr_t)cu_seqlens_bytes != 0 || (reinterpret_cast<uintptr_t>(chunk_states) & 15u)) return GDKVM_ERR_ALIGN;
+    if ((int64_t)n_seqs * params->H > 0x3fffffff) return GDKVM_ERR_SHAPE;
+    if (params->flags & GDKVM_FLAG_FORCE_RECURRENT) return GDKVM_ERR_UNSUPPORTED;
+    if (params->T == 0) return GDKVM_ERR_SHAPE;
+    if (!gdkvm::chunked_supports(*params) || (params->V != 128 && params->V != 256)) return GDKVM_ERR_UNSUPPORTED;
+    bool sm100 = false;
+    int ce = gdkvm::device_is_sm100(&sm100);
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    if (!sm100) return GDKVM_ERR_ARCH;
+    ce = gdkvm::launch_chunked_varlen(*params, cu_seqlens, cu_seqlens_bytes, n_seqs, reinterpret_cast<cudaStream_t>(cuda_stream), chunk_states);
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    return GDKVM_OK;
+}
+
 int gdkvm_gdr_bwd(const GdkvmGdrBwdParams* p, void* cuda_stream) {
     if (p == nullptr) return GDKVM_ERR_NULL;
     if (p->struct_size != sizeof(GdkvmGdrBwdParams)) return GDKVM_ERR_ABI;
@@ -194,11 +219,28 @@ int gdkvm_gdr_bwd(const GdkvmGdrBwdParams* p, void* cuda_stream) {
     if (!p->q || !p->k || !p->v || !p->g || !p->beta || !p->d_o || !p->chunk_states || !p->dq || !p->dk || !p->dv || !p->dg || !p->dbeta)
         return GDKVM_ERR_NULL;
     if (gdkvm::bwd_unsupported_reason(*p)[0] != '\0') return GDKVM_ERR_UNSUPPORTED;
+    if (p->cu_seqlens != nullptr && (p->B != 1 || p->n_seqs < 1 || (p->cu_seqlens_bytes != 4 && p->cu_seqlens_bytes != 8))) return GDKVM_ERR_SHAPE;
     bool sm100 = false;
     int ce = gdkvm::device_is_sm100(&sm100);
     if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
     if (!sm100) return GDKVM_ERR_ARCH;
     ce = gdkvm::launch_bwd(*p, reinterpret_cast<cudaStream_t>(cuda_stream));
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    return GDKVM_OK;
+}
+
+int gdkvm_qkvgb_project_fwd(const GdkvmProjParams* p, void* cuda_stream) {
+    if (p == nullptr) return GDKVM_ERR_NULL;
+    if (p->struct_size != sizeof(GdkvmProjParams)) return GDKVM_ERR_ABI;
+    if (p->R < 0 || p->D <= 0 || p->H <= 0 || p->K <= 0 || p->V <= 0) return GDKVM_ERR_SHAPE;
+    if (p->R == 0) return GDKVM_OK;
+    if (!p->x || !p->w || !p->q || !p->k || !p->v || !p->g || !p->beta) return GDKVM_ERR_NULL;
+    if (gdkvm::proj_unsupported_reason(*p)[0] != '\0') return GDKVM_ERR_UNSUPPORTED;
+    bool sm100 = false;
+    int ce = gdkvm::device_is_sm100(&sm100);
+    if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
+    if (!sm100) return GDKVM_ERR_ARCH;
+    ce = gdkvm::launch_proj(*p, reinterpret_cast<cudaStream_t>(cuda_stream));
     if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
     return GDKVM_OK;
 }

@@ -175,20 +175,35 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2, m0 = 16 * wm, n64 = 16 * wn, n128 = 32 * wn;
-    const int chain = blockIdx.x, b = chain / p.H, h = chain - b * p.H;
-    const int T = p.T, V = p.V, NC = (T + 63) >> 6;
+    // batched: chain = (clip, head), tokens 0 .. T-1 of clip b.  Packed clips: chain = (sequence, head), rows cu[n] .. cu[n+1]-1
+    // of the one packed clip; chunk-state slot of chunk c = cu[n] / 64 + n + c (gdkvm_gdr.h).
+    const int chain = blockIdx.x, V = p.V;
+    int b = chain / p.H;
+    const int h = chain - b * p.H;
+    int T = p.T;
+    int64_t tok0 = 0, cs_blk0, cs_blk_stride;
+    if (p.cu_seqlens != nullptr) {
+        const int64_t lo = p.cu_seqlens_bytes == 8 ? reinterpret_cast<const long long*>(p.cu_seqlens)[b] : reinterpret_cast<const int*>(p.cu_seqlens)[b];
+        const int64_t hi = p.cu_seqlens_bytes == 8 ? reinterpret_cast<const long long*>(p.cu_seqlens)[b + 1] : reinterpret_cast<const int*>(p.cu_seqlens)[b + 1];
+        tok0 = lo; T = (int)(hi - lo);
+        cs_blk0 = ((lo >> 6) + b) * p.H + h; cs_blk_stride = p.H;
+        b = 0;
+    } else {
+        cs_blk0 = (int64_t)chain * ((T + 63) >> 6); cs_blk_stride = 1;
+    }
+    const int NC = (T + 63) >> 6;
     const float scale = p.scale;
 
-    const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(p.q) + (int64_t)b * p.q_stride[0] + (int64_t)h * p.q_stride[2];
-    const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(p.k) + (int64_t)b * p.k_stride[0] + (int64_t)h * p.k_stride[2];
-    const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(p.v) + (int64_t)b * p.v_stride[0] + (int64_t)h * p.v_stride[2];
-    const __nv_bfloat16* dog = reinterpret_cast<const __nv_bfloat16*>(p.d_o) + (int64_t)b * p.do_stride[0] + (int64_t)h * p.do_stride[2];
-    __nv_bfloat16* dqg = reinterpret_cast<__nv_bfloat16*>(p.dq) + (int64_t)b * p.dq_stride[0] + (int64_t)h * p.dq_stride[2];
-    __nv_bfloat16* dkg = reinterpret_cast<__nv_bfloat16*>(p.dk) + (int64_t)b * p.dk_stride[0] + (int64_t)h * p.dk_stride[2];
-    __nv_bfloat16* dvg = reinterpret_cast<__nv_bfloat16*>(p.dv) + (int64_t)b * p.dv_stride[0] + (int64_t)h * p.dv_stride[2];
-    const __nv_bfloat16* sg = reinterpret_cast<const __nv_bfloat16*>(p.chunk_states) + (int64_t)chain * NC * V * 64;
-    const int64_t g_off = (int64_t)b * p.g_stride[0] + (int64_t)h * p.g_stride[2];
-    const int64_t bt_off = (int64_t)b * p.beta_stride[0] + (int64_t)h * p.beta_stride[2];
+    const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(p.q) + (int64_t)b * p.q_stride[0] + (int64_t)h * p.q_stride[2] + tok0 * p.q_stride[1];
+    const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(p.k) + (int64_t)b * p.k_stride[0] + (int64_t)h * p.k_stride[2] + tok0 * p.k_stride[1];
+    const __nv_bfloat16* vg = reinterpret_cast<const __nv_bfloat16*>(p.v) + (int64_t)b * p.v_stride[0] + (int64_t)h * p.v_stride[2] + tok0 * p.v_stride[1];
+    const __nv_bfloat16* dog = reinterpret_cast<const __nv_bfloat16*>(p.d_o) + (int64_t)b * p.do_stride[0] + (int64_t)h * p.do_stride[2] + tok0 * p.do_stride[1];
+    __nv_bfloat16* dqg = reinterpret_cast<__nv_bfloat16*>(p.dq) + (int64_t)b * p.dq_stride[0] + (int64_t)h * p.dq_stride[2] + tok0 * p.dq_stride[1];
+    __nv_bfloat16* dkg = reinterpret_cast<__nv_bfloat16*>(p.dk) + (int64_t)b * p.dk_stride[0] + (int64_t)h * p.dk_stride[2] + tok0 * p.dk_stride[1];
+    __nv_bfloat16* dvg = reinterpret_cast<__nv_bfloat16*>(p.dv) + (int64_t)b * p.dv_stride[0] + (int64_t)h * p.dv_stride[2] + tok0 * p.dv_stride[1];
+    const __nv_bfloat16* sg = reinterpret_cast<const __nv_bfloat16*>(p.chunk_states);
+    const int64_t g_off = (int64_t)b * p.g_stride[0] + (int64_t)h * p.g_stride[2] + tok0 * p.g_stride[1];
+    const int64_t bt_off = (int64_t)b * p.beta_stride[0] + (int64_t)h * p.beta_stride[2] + tok0 * p.beta_stride[1];
 
     // state cotangent dS [64 key dims x V], fp32, in registers: warp (wm, wn) owns rows 16 wm .. + 15, columns 32 wn .. + 31 of
     // each 128-column half
@@ -214,7 +229,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
         load_tile<LD64>(smem + oQ, sb + oQ, qg + (int64_t)t0 * p.q_stride[1], p.q_stride[1], 64, valid, 64, tid);
         load_tile<LD128>(smem + oV, sb + oV, vg + (int64_t)t0 * p.v_stride[1], p.v_stride[1], 64, valid, 128, tid);
         load_tile<LD128>(smem + odO, sb + odO, dog + (int64_t)t0 * p.do_stride[1], p.do_stride[1], 64, valid, 128, tid);
-        load_tile<LD64>(smem + oS, sb + oS, sg + (int64_t)c * V * 64, 64, 128, min(128, V), 64, tid);
+        const __nv_bfloat16* sc_ptr = sg + (cs_blk0 + (int64_t)c * cs_blk_stride) * V * 64;       // chunk-start state [V][64]
+        load_tile<LD64>(smem + oS, sb + oS, sc_ptr, 64, 128, min(128, V), 64, tid);
         if (warp == 0) {        // gates of the chunk: lane l holds tokens 2l, 2l + 1; pad tokens g = 0, beta = 0 (exact no-ops)
             float gv[2], bv[2];
 #pragma unroll
@@ -326,7 +342,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
             if (hh > 0) {        // second value half through the same tiles
                 load_tile<LD128>(smem + oV, sb + oV, vg + (int64_t)t0 * p.v_stride[1] + 128, p.v_stride[1], 64, valid, 128, tid);
                 load_tile<LD128>(smem + odO, sb + odO, dog + (int64_t)t0 * p.do_stride[1] + 128, p.do_stride[1], 64, valid, 128, tid);
-                load_tile<LD64>(smem + oS, sb + oS, sg + ((int64_t)c * V + 128) * 64, 64, 128, 128, 64, tid);
+                load_tile<LD64>(smem + oS, sb + oS, sc_ptr + 128 * 64, 64, 128, 128, 64, tid);
                 cp_async_commit_wait();
                 __syncthreads();
             }
@@ -565,7 +581,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
                     const float u = __shfl_down_sync(0xffffffffu, s, off);
                     if (lane + off < 32) s += u;
                 }
-                const int64_t o0 = ((int64_t)b * T + t0 + 2 * lane) * p.H + h;
+                const int64_t o0 = ((int64_t)b * p.T + tok0 + t0 + 2 * lane) * p.H + h;
                 if (2 * lane < valid) { p.dg[o0] = s; p.dbeta[o0] = sdBt[2 * lane]; }
                 if (2 * lane + 1 < valid) { p.dg[o0 + p.H] = s - x0; p.dbeta[o0 + p.H] = sdBt[2 * lane + 1]; }
             }
@@ -618,7 +634,7 @@ int launch_bwd(const GdkvmGdrBwdParams& p, cudaStream_t stream) {
             if (dev >= 0 && dev < 64) attr_ok[dev] = true;
         }
     }
-    const int chains = p.B * p.H;
+    const int chains = (p.cu_seqlens != nullptr ? p.n_seqs : p.B) * p.H;
     if (p.V > 128) gdr_bwd_kernel<2><<<chains, kBwdThreads, kBwdSmem + 1024, stream>>>(p);
     else gdr_bwd_kernel<1><<<chains, kBwdThreads, kBwdSmem + 1024, stream>>>(p);
     count_launch();

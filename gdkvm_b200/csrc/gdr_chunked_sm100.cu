@@ -321,6 +321,7 @@ struct FastDiv {
 
 // work-unit table of the packed variable-length call: utab[0] = number of entries, entry e at utab + 8 + 8 e:
 // [0] sequence [1] first token (row of the packed stream) [2] valid tokens [3] chunks [4] segment [5] last segment
+// [6] chunk-state slot of the first chunk (training forward)
 constexpr int kUnitInts = 8;
 
 template <bool kVar>
@@ -366,7 +367,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             if (entry < utab[0]) {
                 const int* e = utab + kUnitInts * (1 + entry);
                 s_info[0] = e[4]; s_info[1] = e[0] * p.H + head; s_info[2] = 0; s_info[3] = head;
-                s_info[4] = e[1]; s_info[5] = e[3]; s_info[6] = e[2]; s_info[7] = e[5];
+                s_info[4] = e[1]; s_info[5] = e[3]; s_info[6] = e[2]; s_info[7] = e[5]; s_info[8] = e[6];
             }
         }
         __syncthreads();
@@ -731,12 +732,14 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                             pk[16 + j] = pack_bf16(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1]));
                         }
                         tmem_st32(lane_addr + kColSb + hh * 32, pk);
-                        if (!kVar && sdump != nullptr) {
+                        if (sdump != nullptr) {
                             // training forward: the bf16 chunk-start state (exactly the operand copy Sb) is kept for the backward
-                            // pass, [chain][chunk][value column][key dim] -- 128 contiguous bytes per thread
-                            const int m = (int)s_info[4] + n;
-                            if (m < nc_chain && vcol < V) {
-                                uint4* dst = reinterpret_cast<uint4*>(sdump + (((int64_t)s_info[1] * nc_chain + m) * V + vcol) * 64);
+                            // pass -- batched: [chain][chunk][value column][key dim]; packed clips: [slot][head][value column][key dim]
+                            // -- 128 contiguous bytes per thread
+                            const int m = kVar ? n : (int)s_info[4] + n;
+                            if ((kVar || m < nc_chain) && vcol < V) {
+                                const int64_t blk = kVar ? ((int64_t)s_info[8] + n) * p.H + s_info[3] : (int64_t)s_info[1] * nc_chain + m;
+                                uint4* dst = reinterpret_cast<uint4*>(sdump + (blk * V + vcol) * 64);
 #pragma unroll
                                 for (int j = 0; j < 8; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                             }
@@ -1172,7 +1175,8 @@ __global__ void __launch_bounds__(256) gdr_units_kernel(const IdxT* __restrict__
                 e[0] = n; e[1] = (int)(t0 + (long long)first * 64);
                 e[2] = last ? (int)rest : sc * 64;
                 e[3] = last ? (int)((rest + 63) >> 6) : sc;
-                e[4] = lvl; e[5] = last ? 1 : 0; e[6] = 0; e[7] = 0;
+                e[4] = lvl; e[5] = last ? 1 : 0; e[7] = 0;
+                e[6] = (int)(t0 >> 6) + n + first;      // training forward: chunk-state slot of the unit's first chunk (unique: see gdkvm_gdr.h)
             }
             __syncthreads();
             if (tid == 0) s_base += total;
@@ -1253,7 +1257,7 @@ int chunked_varlen_seg_chunks(const GdkvmGdrParams& p, int nseq, int sms) {
 
 // Packed variable-length sequences: q,k,v,o [1, T, H, *], sequence n = rows cu[n] .. cu[n+1]-1 (offsets on the device,
 // int32 or int64), states [nseq, H, K, V].
-int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream) {
+int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream, void* chunk_states) {
     const DeviceCtx* dc = device_ctx();
     if (dc == nullptr) return (int)cudaErrorInvalidDevice;
     if (dc->attr_err != cudaSuccess) return (int)dc->attr_err;
@@ -1285,7 +1289,7 @@ int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes,
                                                      p.initial_state, p.final_state);
     count_launch();
     gdr_chunk_kernel<true><<<max_entries * H, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, p.T, 1, FastDiv::make(1u), 0, 0, xstate,
-                                                                              xsync, utab, nullptr);
+                                                                              xsync, utab, reinterpret_cast<__nv_bfloat16*>(chunk_states));
     count_launch();
     const cudaError_t le = cudaGetLastError();
     cudaFreeAsync(ws, stream);

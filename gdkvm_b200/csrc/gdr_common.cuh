@@ -15,7 +15,8 @@ int launch_recurrent(const GdkvmGdrParams& p, cudaStream_t stream);
 int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream, void* chunk_states = nullptr);
 // Packed variable-length sequences (q,k,v,o [1, T, H, *]; device-resident offsets cu[0..nseq], cu_bytes = 4 | 8; states [nseq, H, K, V])
 int launch_recurrent_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream);
-int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream);
+// chunk_states != nullptr: training forward, [T / 64 + nseq + 1 slots][H][V][K] bf16, slot of chunk c of clip n = cu[n] / 64 + n + c
+int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes, int nseq, cudaStream_t stream, void* chunk_states = nullptr);
 int launch_l2norm(const void* x, void* y, int64_t rows, int D, int64_t xs, int64_t ys, int dtype, float eps, cudaStream_t stream);
 // Host-side eligibility test of the chunked tcgen05 kernel (no GPU needed).
 bool chunked_supports(const GdkvmGdrParams& p);
@@ -27,6 +28,10 @@ int chunked_segments(const GdkvmGdrParams& p, int sms);
 // Backward pass (gdr_bwd_sm100.cu)
 int launch_bwd(const GdkvmGdrBwdParams& p, cudaStream_t stream);
 const char* bwd_unsupported_reason(const GdkvmGdrBwdParams& p);
+
+// Fused projection prologue (gdr_proj_sm100.cu)
+int launch_proj(const GdkvmProjParams& p, cudaStream_t stream);
+const char* proj_unsupported_reason(const GdkvmProjParams& p);
 
 void count_launch();
 

@@ -24,7 +24,7 @@ import torch
 
 from . import _cabi
 
-__all__ = ["gdr_lkva", "gdr_lkva_out", "train_unsupported_reason", "gdr_lkva_varlen", "gdr_lkva_varlen_out", "check_inputs", "chunk_gated_delta_rule", "l2norm", "plan", "plan_reason",
+__all__ = ["gdr_lkva", "gdr_lkva_out", "train_unsupported_reason", "qkvgb_project", "qkvgb_project_reference", "gdr_lkva_varlen", "gdr_lkva_varlen_out", "check_inputs", "chunk_gated_delta_rule", "l2norm", "plan", "plan_reason",
            "plan_segments", "launch_count"]
 
 _DT = {torch.float32: _cabi.GDKVM_F32, torch.bfloat16: _cabi.GDKVM_BF16}
@@ -177,7 +177,12 @@ torch.library.define(
 torch.library.define(
     "gdkvm::gdr_lkva_bwd",
     "(Tensor q, Tensor k, Tensor v, Tensor g, Tensor beta, Tensor chunk_states, Tensor d_o, Tensor? d_final_state, float scale, "
-    "bool need_d_initial_state) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)",
+    "bool need_d_initial_state, Tensor? cu_seqlens=None) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)",
+)
+torch.library.define(
+    "gdkvm::gdr_lkva_varlen_train",
+    "(Tensor q, Tensor k, Tensor v, Tensor g, Tensor beta, Tensor cu_seqlens, float? scale=None, Tensor? initial_state=None, "
+    "int flags=0) -> (Tensor, Tensor, Tensor)",
 )
 
 
@@ -230,24 +235,25 @@ def _gdr_lkva_train_fake(q, k, v, g, beta, scale=None, initial_state=None, flags
 
 
 @torch.library.impl("gdkvm::gdr_lkva_bwd", "CUDA")
-def _gdr_lkva_bwd_cuda(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale, need_d_initial_state):
+def _gdr_lkva_bwd_cuda(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale, need_d_initial_state, cu_seqlens=None):
     _check(q, k, v, g, beta, None)
-    _same_device(q, chunk_states=chunk_states, d_o=d_o, d_final_state=d_final_state)
+    _same_device(q, chunk_states=chunk_states, d_o=d_o, d_final_state=d_final_state, cu_seqlens=cu_seqlens)
     B, T, H, K = k.shape
     V = v.shape[-1]
+    NS = B if cu_seqlens is None else cu_seqlens.numel() - 1          # number of states: clips, or packed clips
     if d_o.shape != v.shape or d_o.dtype != q.dtype:
         raise ValueError("d_o must have the shape and dtype of the readout")
     if d_o.stride(-1) != 1:
         d_o = d_o.contiguous()
     if d_final_state is not None:
-        if d_final_state.shape != (B, H, K, V):
-            raise ValueError("d_final_state must be [B,H,K,V]")
+        if d_final_state.shape != (NS, H, K, V):
+            raise ValueError("d_final_state must be [B,H,K,V] ([n_seqs,H,K,V] for packed clips)")
         d_final_state = d_final_state.to(torch.float32).contiguous()
     dq, dk, dv = torch.empty_like(q, memory_format=torch.contiguous_format), torch.empty_like(k, memory_format=torch.contiguous_format), \
         torch.empty_like(v, memory_format=torch.contiguous_format)
     dg = torch.empty((B, T, H), dtype=torch.float32, device=q.device)
     db = torch.empty((B, T, H), dtype=torch.float32, device=q.device)
-    ds0 = torch.empty((B, H, K, V) if need_d_initial_state else (0,), dtype=torch.float32, device=q.device)
+    ds0 = torch.empty((NS, H, K, V) if need_d_initial_state else (0,), dtype=torch.float32, device=q.device)
     if T == 0:
         if need_d_initial_state:
             ds0.copy_(d_final_state) if d_final_state is not None else ds0.zero_()
@@ -266,6 +272,9 @@ def _gdr_lkva_bwd_cuda(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale
     p.dq_stride, p.dk_stride, p.dv_stride = _strides3(dq), _strides3(dk), _strides3(dv)
     p.B, p.T, p.H, p.K, p.V = B, T, H, K, V
     p.io_dtype, p.gate_dtype, p.scale = _DT[q.dtype], _DT[g.dtype], float(scale)
+    if cu_seqlens is not None:
+        cu = cu_seqlens.contiguous()
+        p.cu_seqlens, p.cu_seqlens_bytes, p.n_seqs = cu.data_ptr(), cu.element_size(), NS
     with torch.cuda.device(q.device):
         rc = lib.gdkvm_gdr_bwd(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     if rc != 0:
@@ -275,12 +284,75 @@ def _gdr_lkva_bwd_cuda(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale
 
 
 @torch.library.register_fake("gdkvm::gdr_lkva_bwd")
-def _gdr_lkva_bwd_fake(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale, need_d_initial_state):
+def _gdr_lkva_bwd_fake(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale, need_d_initial_state, cu_seqlens=None):
     B, T, H, K = k.shape
     V = v.shape[-1]
+    NS = B if cu_seqlens is None else cu_seqlens.shape[0] - 1
     f32 = dict(dtype=torch.float32)
     return (torch.empty_like(q), torch.empty_like(k), torch.empty_like(v), q.new_empty((B, T, H), **f32), q.new_empty((B, T, H), **f32),
-            q.new_empty((B, H, K, V) if need_d_initial_state else (0,), **f32))
+            q.new_empty((NS, H, K, V) if need_d_initial_state else (0,), **f32))
+
+
+@torch.library.impl("gdkvm::gdr_lkva_varlen_train", "CUDA")
+def _gdr_lkva_varlen_train_cuda(q, k, v, g, beta, cu_seqlens, scale=None, initial_state=None, flags=0):
+    _check(q, k, v, g, beta, None)
+    _same_device(q, cu_seqlens=cu_seqlens, initial_state=initial_state)
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    why = train_unsupported_reason(q, k, v)
+    if why:
+        raise NotImplementedError(f"gdkvm_b200 training forward: {why}")
+    if B != 1 or cu_seqlens.dim() != 1 or cu_seqlens.numel() < 2 or cu_seqlens.dtype not in (torch.int32, torch.int64):
+        raise ValueError("packed clips: q,k,v [1, total_tokens, H, *] and cu_seqlens int32/int64 [n_seqs + 1]")
+    N = cu_seqlens.numel() - 1
+    cu = cu_seqlens.contiguous()
+    if initial_state is not None:
+        if initial_state.shape != (N, H, K, V) or initial_state.dtype != torch.float32:
+            raise ValueError("initial_state must be fp32 [n_seqs,H,K,V]")
+        initial_state = initial_state.contiguous()
+    lib = _cabi.load()
+    o = torch.empty((1, T, H, V), dtype=q.dtype, device=q.device)
+    sT = torch.empty((N, H, K, V), dtype=torch.float32, device=q.device)
+    cs = torch.empty((T // 64 + N + 1, H, V, K), dtype=torch.bfloat16, device=q.device)
+    assert cs.numel() * 2 == lib.gdkvm_gdr_chunk_states_bytes_varlen(T, N, H, K, V)
+    if T == 0:
+        sT.copy_(initial_state) if initial_state is not None else sT.zero_()
+        return o, sT, cs
+    if scale is None:
+        scale = 1.0 / math.sqrt(K)
+    p = _make_params(q, k, v, g, beta, o, initial_state, sT, scale, 0, flags & ~0xF)
+    with torch.cuda.device(q.device):
+        rc = lib.gdkvm_gdr_fwd_train_varlen(ctypes.byref(p), ctypes.c_void_p(cu.data_ptr()), cu.element_size(), N,
+                                            ctypes.c_void_p(cs.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        extra = f" (cudaError {lib.gdkvm_last_cuda_error()})" if rc == -7 else ""
+        raise RuntimeError(f"gdkvm_gdr_fwd_train_varlen: {_cabi.strerror(rc)}{extra}")
+    return o, sT, cs
+
+
+@torch.library.register_fake("gdkvm::gdr_lkva_varlen_train")
+def _gdr_lkva_varlen_train_fake(q, k, v, g, beta, cu_seqlens, scale=None, initial_state=None, flags=0):
+    B, T, H, K = k.shape
+    V = v.shape[-1]
+    N = cu_seqlens.shape[0] - 1
+    return (q.new_empty((1, T, H, V)), q.new_empty((N, H, K, V), dtype=torch.float32),
+            q.new_empty((T // 64 + N + 1, H, V, K), dtype=torch.bfloat16))
+
+
+def _vtrain_setup(ctx, inputs, output):
+    q, k, v, g, beta, cu_seqlens, scale, initial_state, flags = inputs
+    ctx.save_for_backward(q, k, v, g, beta, output[2], cu_seqlens)
+    ctx.scale = scale if scale is not None else 1.0 / math.sqrt(k.shape[-1])
+    ctx.has_s0 = initial_state is not None
+    ctx.set_materialize_grads(False)
+
+
+def _vtrain_backward(ctx, d_o, d_sT, _d_cs):
+    q, k, v, g, beta, cs, cu = ctx.saved_tensors
+    if d_o is None:
+        d_o = torch.zeros_like(v)
+    dq, dk, dv, dg, db, ds0 = torch.ops.gdkvm.gdr_lkva_bwd(q, k, v, g, beta, cs, d_o.to(q.dtype), d_sT, ctx.scale, ctx.has_s0, cu)
+    return dq, dk, dv, dg.to(g.dtype), db.to(beta.dtype), None, None, (ds0 if ctx.has_s0 else None), None
 
 
 def _train_setup(ctx, inputs, output):
@@ -300,14 +372,15 @@ def _train_backward(ctx, d_o, d_sT, _d_cs):
 
 
 torch.library.register_autograd("gdkvm::gdr_lkva_train", _train_backward, setup_context=_train_setup)
+torch.library.register_autograd("gdkvm::gdr_lkva_varlen_train", _vtrain_backward, setup_context=_vtrain_setup)
 
 
 def _no_backward(name):
     def backward(ctx, *grads):
         raise NotImplementedError(
             f"torch.ops.gdkvm.{name} has no backward formula: differentiate through gdkvm_b200.gdr_lkva / GDRMemory / "
-            "chunk_gated_delta_rule (they route a call that needs gradients to the training forward, bf16, d_k = 64, "
-            "d_v in {128, 256}); packed variable-length clips are forward-only")
+            "gdr_lkva_varlen / chunk_gated_delta_rule (they route a call that needs gradients to the training forward: bf16, "
+            "d_k = 64, d_v in {128, 256})")
     return backward
 
 
@@ -422,6 +495,101 @@ def _l2norm_backward(ctx, dy):
 torch.library.register_autograd("gdkvm::l2norm", _l2norm_backward, setup_context=_l2norm_setup)
 
 
+torch.library.define("gdkvm::qkvgb_project",
+                     "(Tensor x, Tensor weight, Tensor? bias, int heads, int d_k, int d_v, float eps=1e-6) -> (Tensor, Tensor, Tensor, Tensor, Tensor)")
+
+
+@torch.library.impl("gdkvm::qkvgb_project", "CUDA")
+def _qkvgb_project_cuda(x, weight, bias, heads, d_k, d_v, eps=1e-6):
+    H, K, V = int(heads), int(d_k), int(d_v)
+    N = H * (2 * K + V) + 2 * H
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise TypeError("qkvgb_project: features and weight must be bfloat16")
+    if weight.dim() != 2 or weight.shape[0] != N or weight.shape[1] != x.shape[-1]:
+        raise ValueError(f"qkvgb_project: weight must be [H (2 d_k + d_v) + 2 H = {N}, D = {x.shape[-1]}] (rows q | k | v | g | beta)")
+    _same_device(x, weight=weight, bias=bias)
+    D = x.shape[-1]
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, D)
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    w = weight.contiguous()
+    if bias is not None:
+        if bias.shape != (N,):
+            raise ValueError("qkvgb_project: bias must be [N]")
+        bias = bias.to(torch.float32).contiguous()
+    R = x2.shape[0]
+    dev = x.device
+    q = torch.empty(*lead, H, K, dtype=torch.bfloat16, device=dev)
+    k = torch.empty(*lead, H, K, dtype=torch.bfloat16, device=dev)
+    v = torch.empty(*lead, H, V, dtype=torch.bfloat16, device=dev)
+    g = torch.empty(*lead, H, dtype=torch.float32, device=dev)
+    beta = torch.empty(*lead, H, dtype=torch.float32, device=dev)
+    p = _cabi.GdkvmProjParams()
+    p.struct_size = ctypes.sizeof(_cabi.GdkvmProjParams)
+    p.x, p.w, p.bias = x2.data_ptr(), w.data_ptr(), (bias.data_ptr() if bias is not None else None)
+    p.q, p.k, p.v, p.g, p.beta = q.data_ptr(), k.data_ptr(), v.data_ptr(), g.data_ptr(), beta.data_ptr()
+    p.R, p.x_row_stride, p.D, p.H, p.K, p.V, p.eps = R, x2.stride(0), D, H, K, V, float(eps)
+    lib = _cabi.load()
+    with torch.cuda.device(dev):
+        rc = lib.gdkvm_qkvgb_project_fwd(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc != 0:
+        extra = f" (cudaError {lib.gdkvm_last_cuda_error()})" if rc == -7 else ""
+        raise RuntimeError(f"gdkvm_qkvgb_project_fwd: {_cabi.strerror(rc)}{extra}")
+    return q, k, v, g, beta
+
+
+@torch.library.register_fake("gdkvm::qkvgb_project")
+def _qkvgb_project_fake(x, weight, bias, heads, d_k, d_v, eps=1e-6):
+    lead = x.shape[:-1]
+    f32 = dict(dtype=torch.float32)
+    return (x.new_empty(*lead, heads, d_k), x.new_empty(*lead, heads, d_k), x.new_empty(*lead, heads, d_v),
+            x.new_empty(*lead, heads, **f32), x.new_empty(*lead, heads, **f32))
+
+
+def qkvgb_project_reference(x, weight, bias, heads, d_k, d_v, eps=1e-6):
+    """The same map in plain torch ops (library GEMM + elementwise passes): the unfused route bench.py times the fused kernel
+    against, and the formula autograd differentiates in the backward of ``qkvgb_project``."""
+    H, K, V = heads, d_k, d_v
+    y = torch.nn.functional.linear(x, weight, bias.to(x.dtype) if bias is not None else None).float()
+    lead = x.shape[:-1]
+    yq, yk, yv, yg, yb = torch.split(y, [H * K, H * K, H * V, H, H], dim=-1)
+    nrm = lambda t: (t.reshape(*lead, H, K) * torch.rsqrt(t.reshape(*lead, H, K).square().sum(-1, keepdim=True) + eps))
+    return (nrm(yq).to(x.dtype), nrm(yk).to(x.dtype), yv.reshape(*lead, H, V).to(x.dtype),
+            torch.nn.functional.logsigmoid(yg), torch.sigmoid(yb))
+
+
+def _proj_setup(ctx, inputs, output):
+    x, weight, bias, heads, d_k, d_v, eps = inputs
+    ctx.save_for_backward(x, weight, bias)
+    ctx.cfg = (heads, d_k, d_v, eps)
+
+
+def _proj_backward(ctx, dq, dk, dv, dg, db):
+    # recompute through the torch formula (library GEMMs): training goes through cuBLAS here, inference through the fused kernel
+    x, weight, bias = ctx.saved_tensors
+    with torch.enable_grad():
+        xs = x.detach().requires_grad_(True)
+        ws = weight.detach().requires_grad_(True)
+        bs = bias.detach().requires_grad_(True) if bias is not None else None
+        outs = qkvgb_project_reference(xs, ws, bs, *ctx.cfg)
+        pairs = [(o, d) for o, d in zip(outs, (dq, dk, dv, dg, db)) if d is not None]
+        gr = torch.autograd.grad([o for o, _ in pairs], [xs, ws] + ([bs] if bs is not None else []), [d for _, d in pairs], allow_unused=True)
+    return gr[0], gr[1], (gr[2] if bs is not None else None), None, None, None, None
+
+
+torch.library.register_autograd("gdkvm::qkvgb_project", _proj_backward, setup_context=_proj_setup)
+
+
+def qkvgb_project(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], heads: int, d_k: int = 64, d_v: int = 256,
+                  eps: float = 1e-6):
+    """Fused projection prologue of the memory op: ``x [..., D]`` (bf16) times ``weight [H (2 d_k + d_v) + 2 H, D]`` (rows ordered
+    q | k | v | g | beta) in one tcgen05 GEMM whose epilogue L2-normalises q and k per head, applies logsigmoid / sigmoid to
+    the gate / beta columns and writes ``(q, k [..., H, d_k], v [..., H, d_v]`` bf16, ``g, beta [..., H]`` fp32) -- exactly
+    the operands of ``gdr_lkva`` (reference: KPFF, website/src/content/homepage/en.json:20)."""
+    return torch.ops.gdkvm.qkvgb_project(x, weight, bias, heads, d_k, d_v, eps)
+
+
 def l2norm(x: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     """Row-wise ``x * rsqrt(sum(x^2, -1) + eps)`` on the B200 (the q/k normalisation in front of the memory op;
     fla's ``use_qk_l2norm_in_kernel``, fla/ops/gated_delta_rule/chunk.py:374).  D in {32, 64, 128, 256}."""
@@ -461,6 +629,12 @@ def gdr_lkva_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, g: torch.
     cu_seqlens[n] .. cu_seqlens[n+1]-1); initial_state fp32 [N,H,K,V].  Returns ``(o [1,T,H,V], final_state [N,H,K,V] or
     None)``.  Nothing is read back to the host: the work-unit table is built on the device.
     """
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (q, k, v, g, beta, initial_state)):
+        why = train_unsupported_reason(q, k, v)
+        if why:
+            raise NotImplementedError(f"gdkvm_b200.gdr_lkva_varlen cannot be differentiated for these tensors: {why}")
+        o, sT, _ = torch.ops.gdkvm.gdr_lkva_varlen_train(q, k, v, g, beta, cu_seqlens, scale, initial_state, flags)
+        return o, (sT if output_final_state else None)
     o, sT = torch.ops.gdkvm.gdr_lkva_varlen(q, k, v, g, beta, cu_seqlens, scale, initial_state, output_final_state, flags)
     return o, (sT if output_final_state else None)
 

@@ -178,6 +178,14 @@ int gdkvm_l2norm_fwd(const void* x, void* y, int64_t rows, int32_t D, int64_t x_
  */
 int gdkvm_gdr_fwd_train(const GdkvmGdrParams* params, void* chunk_states, void* cuda_stream);
 int64_t gdkvm_gdr_chunk_states_bytes(int32_t B, int32_t T, int32_t H, int32_t K, int32_t V);
+/*
+ * The same for packed variable-length clips (gdkvm_gdr_fwd_varlen's arguments): chunk_states holds
+ * gdkvm_gdr_chunk_states_bytes_varlen(T, n_seqs, H, K, V) bytes laid out [T / 64 + n_seqs + 1 slots][H][V][K]; chunk c of clip n
+ * uses slot cu_seqlens[n] / 64 + n + c (distinct for distinct chunks, computable without a scan over the offsets).
+ */
+int gdkvm_gdr_fwd_train_varlen(const GdkvmGdrParams* params, const void* cu_seqlens, int32_t cu_seqlens_bytes, int32_t n_seqs,
+                               void* chunk_states, void* cuda_stream);
+int64_t gdkvm_gdr_chunk_states_bytes_varlen(int32_t T, int32_t n_seqs, int32_t H, int32_t K, int32_t V);
 
 /*
  * Gradients of (readout, final_state) with respect to (q, k, v, g, beta, initial_state), given the cotangents d_o [B,T,H,V]
@@ -215,9 +223,46 @@ typedef struct GdkvmGdrBwdParams {
     int32_t io_dtype;
     int32_t gate_dtype;
     float scale;
+    /* packed variable-length clips (the backward of gdkvm_gdr_fwd_train_varlen): B = 1, T = total tokens, states and their
+       cotangents [n_seqs, H, K, V]; NULL / 0 / 0 for the batched call */
+    const void* cu_seqlens;      /* device, n_seqs + 1 offsets                                 */
+    int32_t cu_seqlens_bytes;    /* 4 or 8                                                     */
+    int32_t n_seqs;
 } GdkvmGdrBwdParams;
 
 int gdkvm_gdr_bwd(const GdkvmGdrBwdParams* params, void* cuda_stream);
+
+/*
+ * ---- fused projection prologue: features -> the op's operands in ONE kernel ----
+ *   replaces: the projections that turn the fused key/pixel feature into q, k, v, gate, beta ("Key-Pixel Feature Fusion fuses
+ *   the local key feature, the global key feature with the pixel feature", reference website/src/content/homepage/en.json:20)
+ *   plus the q/k L2 normalisation (fla/ops/gated_delta_rule/chunk.py:374) and the gate / beta activations.
+ *
+ *   y = x w^T (+ bias),  x [R, D] bf16 (row stride in elements),  w [N, D] bf16 row-major (the nn.Linear layout),
+ *   N = H (2 K + V) + 2 H with the rows of w ordered   q (H x K) | k (H x K) | v (H x V) | g (H) | beta (H);
+ *   q, k <- y_q, y_k L2-normalised per head (x rsqrt(sum x^2 + eps)) -> bf16 [R, H, K];   v <- y_v -> bf16 [R, H, V];
+ *   g <- logsigmoid(y_g), beta <- sigmoid(y_beta) -> fp32 [R, H].   K = 64, H even (2..32), V % 64 == 0, D % 64 == 0.
+ * A tcgen05 GEMM (TMA-staged operands, TMEM accumulators) whose epilogue writes the op-ready tensors: y never touches HBM.
+ */
+typedef struct GdkvmProjParams {
+    uint32_t struct_size;        /* = sizeof(GdkvmProjParams)                                  */
+    uint32_t flags;              /* reserved, 0                                                */
+    const void* x;
+    const void* w;
+    const float* bias;           /* [N] fp32, may be NULL                                      */
+    void* q;
+    void* k;
+    void* v;
+    float* g;
+    float* beta;
+    int64_t R;                   /* rows = tokens (B * T)                                      */
+    int64_t x_row_stride;        /* elements                                                   */
+    int32_t D, H, K, V;
+    float eps;
+    int32_t reserved;
+} GdkvmProjParams;
+
+int gdkvm_qkvgb_project_fwd(const GdkvmProjParams* params, void* cuda_stream);
 
 /* Number of kernels this library has launched in the calling process (bench "gpu_launches"). */
 uint64_t gdkvm_launch_count(void);

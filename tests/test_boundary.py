@@ -29,20 +29,48 @@ def test_header_symbols_exported(built_lib):
     assert lib.gdkvm_abi_version() == _cabi.GDKVM_ABI_VERSION
 
 
-def test_struct_layout_matches_header(built_lib, tmp_path):
+@pytest.mark.parametrize("struct", ["GdkvmGdrParams", "GdkvmGdrBwdParams", "GdkvmProjParams"])
+def test_struct_layout_matches_header(built_lib, tmp_path, struct):
     """Compile a probe against the real header with gcc and compare size/offsets with ctypes."""
     from gdkvm_b200 import _cabi
-    fields = [f[0] for f in _cabi.GdkvmGdrParams._fields_]
-    body = "".join(f'printf("{f} %zu\\n", offsetof(GdkvmGdrParams, {f}));' for f in fields)
+    cls = getattr(_cabi, struct)
+    fields = [f[0] for f in cls._fields_]
+    body = "".join(f'printf("{f} %zu\\n", offsetof({struct}, {f}));' for f in fields)
     c = tmp_path / "probe.c"
     c.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "gdkvm_gdr.h"\n'
-                 'int main(void){printf("sizeof %zu\\n", sizeof(GdkvmGdrParams));' + body + 'return 0;}')
+                 'int main(void){printf("sizeof %zu\\n", sizeof(' + struct + '));' + body + 'return 0;}')
     exe = tmp_path / "probe"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(c), "-o", str(exe)])
     out = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
-    assert int(out["sizeof"]) == ctypes.sizeof(_cabi.GdkvmGdrParams)
+    assert int(out["sizeof"]) == ctypes.sizeof(cls)
     for f in fields:
-        assert int(out[f]) == getattr(_cabi.GdkvmGdrParams, f).offset, f
+        assert int(out[f]) == getattr(cls, f).offset, f
+
+
+def test_training_and_projection_entry_points_validate_without_gpu(built_lib):
+    from gdkvm_b200 import _cabi
+    lib = _cabi.load()
+    assert lib.gdkvm_gdr_chunk_states_bytes(64, 6272, 8, 64, 256) == 64 * 8 * 98 * 256 * 64 * 2
+    assert lib.gdkvm_gdr_chunk_states_bytes(1, 65, 1, 64, 128) == 2 * 128 * 64 * 2 and lib.gdkvm_gdr_chunk_states_bytes(0, 1, 1, 64, 128) == 0
+    bp = _cabi.GdkvmGdrBwdParams()
+    assert lib.gdkvm_gdr_bwd(None, None) == -1 and lib.gdkvm_gdr_bwd(ctypes.byref(bp), None) == -2       # NULL, ABI guard
+    bp.struct_size = ctypes.sizeof(bp)
+    bp.B = bp.T = bp.H = 1; bp.K = 64; bp.V = 128; bp.io_dtype = 1
+    assert lib.gdkvm_gdr_bwd(ctypes.byref(bp), None) == -1                                              # tensors missing
+    pp = _cabi.GdkvmProjParams()
+    assert lib.gdkvm_qkvgb_project_fwd(ctypes.byref(pp), None) == -2
+    pp.struct_size = ctypes.sizeof(pp)
+    pp.R, pp.D, pp.H, pp.K, pp.V = 10, 256, 8, 64, 256
+    assert lib.gdkvm_qkvgb_project_fwd(ctypes.byref(pp), None) == -1
+    buf = torch.zeros(1 << 16, dtype=torch.bfloat16)
+    for n in ("x", "w", "q", "k", "v", "g", "beta"):
+        setattr(pp, n, buf.data_ptr())
+    pp.x_row_stride = 256
+    pp.H = 3
+    assert lib.gdkvm_qkvgb_project_fwd(ctypes.byref(pp), None) == -8                                    # odd head count: unsupported
+    pp.H = 8
+    if not torch.cuda.is_available():
+        assert lib.gdkvm_qkvgb_project_fwd(ctypes.byref(pp), None) in (-6, -7)                           # no device: never a host path
 
 
 def _inputs(B=2, T=98, H=2, K=64, V=256, dtype=torch.bfloat16):

@@ -62,6 +62,34 @@ def test_backward_vs_float64_autograd(op, case):
         assert e <= 2e-2 and r <= 1e-2, (name, e, r)
 
 
+@pytest.mark.parametrize("cu_dtype", [torch.int32, torch.int64], ids=["i32", "i64"])
+def test_backward_of_packed_variable_length_clips(op, cu_dtype):
+    """cu_seqlens call, differentiated: ragged clips, an empty clip, a single token, forced time segments in the forward --
+    every gradient of every clip against float64 autograd over that clip alone."""
+    lens = [200, 0, 64, 1, 333, 17]
+    H, V, T = 2, 256, sum(lens)
+    q, k, v, g, beta, _, do, _ = _case(1, T, H, V, 401)
+    gen = torch.Generator().manual_seed(402)
+    S0 = 0.1 * torch.randn(len(lens), H, 64, V, generator=gen)
+    dsT = torch.randn(len(lens), H, 64, V, generator=gen)
+    cu = torch.tensor([0] + [sum(lens[:i + 1]) for i in range(len(lens))], dtype=cu_dtype)
+    leaf = lambda x: x.cuda().requires_grad_(True)
+    qd, kd, vd, gd, bd, sd = map(leaf, (q, k, v, g, beta, S0))
+    o, sT = op.gdr_lkva_varlen(qd, kd, vd, gd, bd, cu.cuda(), None, sd, True, (3 & 0xF) << 8)
+    ((o.float() * do.cuda().float()).sum() + (sT * dsT.cuda()).sum()).backward()
+    torch.cuda.synchronize()
+    got = [x.grad.float().cpu() for x in (qd, kd, vd, gd, bd, sd)]
+    for n, L in enumerate(lens):
+        a, b = int(cu[n]), int(cu[n + 1])
+        if L == 0:
+            assert torch.equal(got[5][n], dsT[n])                   # an empty clip passes the state cotangent through
+            continue
+        ref = gdr_backward_ref(q[:, a:b], k[:, a:b], v[:, a:b], g[:, a:b], beta[:, a:b], do[:, a:b], dsT[n:n + 1], None, S0[n:n + 1])
+        for name, x, r in zip(NAMES, got, ref):
+            xx = x[n:n + 1] if name == "dS0" else x[:, a:b]
+            assert max_rel_err(xx, r.float()) <= 2e-2, (n, name)
+
+
 def test_training_forward_is_the_inference_forward(op):
     """gdr_lkva_train = the tcgen05 kernel on flat 64-token chunks, bit for bit, plus the bf16 chunk-start states."""
     q, k, v, g, beta, S0, _, _ = _case(3, 5 * 64 + 7, 2, 256, 301)
@@ -109,8 +137,8 @@ def test_what_cannot_be_differentiated_says_so(op):
     with pytest.raises(NotImplementedError, match="no backward formula"):
         o.float().sum().backward()
     cu = torch.tensor([0, 40], dtype=torch.int32, device="cuda")
-    o, _ = op.gdr_lkva_varlen(qb, kb, vb, g.cuda(), beta.cuda(), cu)
-    with pytest.raises(NotImplementedError, match="forward-only"):
+    o, _ = torch.ops.gdkvm.gdr_lkva_varlen(qb, kb, vb, g.cuda(), beta.cuda(), cu)                    # the raw packed inference op
+    with pytest.raises(NotImplementedError, match="no backward formula"):
         o.float().sum().backward()
     with pytest.raises(NotImplementedError):                                                         # d_v = 64
         op.gdr_lkva(qb, kb, vb[..., :64].contiguous().requires_grad_(True), g.cuda(), beta.cuda())
