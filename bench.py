@@ -241,8 +241,23 @@ def fla_child():
     fn = lambda: fla_op(q, k, v, g, beta, initial_state=S0, output_final_state=True)
     t0 = time.time()
     ms, steps, win = time_for(fn, 0.6)
-    print(json.dumps({"ms_per_step": ms, "steps": steps, "value": B * W["frames"] / (ms * 1e-3), "window": win,
-                      "compile_and_run_s": time.time() - t0}), flush=True)
+    out = {"ms_per_step": ms, "steps": steps, "value": B * W["frames"] / (ms * 1e-3), "window": win}
+    try:        # forward + backward through fla's autograd (the comparator of extra.backward)
+        leaves = [x.clone().requires_grad_(True) for x in (q, k, v, g, beta, S0)]
+        d_o = torch.randn_like(v)
+
+        def fb():
+            o, sT = fla_op(*leaves[:5], initial_state=leaves[5], output_final_state=True)
+            torch.autograd.backward([o, sT], [d_o, torch.ones_like(sT)])
+            for x in leaves:
+                x.grad = None
+        ms_fb, _, _ = time_for(fb, 0.6)
+        out["forward_plus_backward_ms"] = ms_fb
+    except Exception as ex:  # noqa: BLE001
+        out["forward_plus_backward_ms"] = None
+        out["backward_failed"] = repr(ex)[:200]
+    out["compile_and_run_s"] = time.time() - t0
+    print(json.dumps(out), flush=True)
 
 
 def run_extras(args, dev, sampler, main_inputs, main_ms):

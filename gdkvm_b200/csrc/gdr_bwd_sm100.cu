@@ -41,18 +41,19 @@ constexpr uint32_t SZ64 = 64 * LD64 * 2;         // 64 x 64 bf16 tile
 constexpr uint32_t SZ128 = 64 * LD128 * 2;       // 64 x 128 bf16 tile
 constexpr uint32_t SZS = 128 * LD64 * 2;         // chunk-start state half [128 values][64 key dims]
 // ---- shared memory map ----
-constexpr uint32_t oK = 0, oQ = oK + SZ64, oQe = oQ + SZ64, oT = oQe + SZ64, oTb = oT + SZ64, oP = oTb + SZ64, oKKD = oP + SZ64,
-                   oWn = oKKD + SZ64, oH = oWn + SZ64;
-constexpr uint32_t oV = oH + 8192, odO = oV + SZ128, oVn = odO + SZ128, odVn = oVn + SZ128, oS = odVn + SZ128, odSb = oS + SZS;
-constexpr uint32_t oF = odSb + SZ128;
-constexpr int kNumF = 6 * 64 + 8;                // Gam, E, Bt, Kd, dGam, dBt, misc
+constexpr uint32_t oKQ = 0;                                      // [2 chunks][K | Q]: the next chunk's tiles are prefetched under the tail
+constexpr uint32_t oQe = oKQ + 4 * SZ64, oT = oQe + SZ64, oTb = oT + SZ64, oP = oTb + SZ64, oKKD = oP + SZ64, oWn = oKKD + SZ64,
+                   oH = oWn + SZ64;
+constexpr uint32_t oV = oH + 8192, odO = oV + SZ128, oVn = odO + SZ128, odVn = oVn + SZ128, oS = odVn + SZ128, odSb = oS + SZS,
+                   odVst = odSb + SZ128;                          // dV staging (leaves through 16-byte global stores)
+constexpr uint32_t oF = odVst + SZ128;
+constexpr int kNumF = 4 * 64 + 3 * 256 + 16 + 8; // Gam, E, Bt, Kd; row / column partial sums of dGamma, dbeta per warp column / row; dGamma_last per warp
 constexpr uint32_t kBwdSmem = oF + kNumF * 4 + 16;
-// after the value halves the four big tiles are dead: the 64 x 64 operands of the tail live there
-constexpr uint32_t odW = oV, odPD = oV + SZ64, odT = oV + 2 * SZ64, oX = oV + 3 * SZ64, oM = oV + 4 * SZ64, oOutQ = oV + 5 * SZ64,
-                   oOutK = oV + 6 * SZ64;
-static_assert(oOutK + SZ64 <= oS, "tail operands must fit into the four value tiles");
+// the 64 x 64 operands of the tail live in tiles that are dead by then -- but NOT in V, dO, S, which take the next chunk's
+// first value half while the tail runs
+constexpr uint32_t odW = oVn, odPD = odVn, odT = odSb, oX = oTb, oM = oWn, oOutQ = oP, oOutK = oQe;
 constexpr uint32_t oTbe = oVn;                   // T diag(beta e): only until W has been formed
-static_assert(kBwdSmem <= 232448, "exceeds the 227 KB dynamic shared memory limit");
+static_assert(kBwdSmem + 1024 <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
@@ -81,17 +82,70 @@ __device__ __forceinline__ void wgemm(float (&acc)[NT][4], uint32_t A, int m0, u
                                : A + (uint32_t)(((m0 + (lane & 15)) * LDA + 8 * (lane >> 4)) * 2);
     const uint32_t b_lane = TB ? B + (uint32_t)((((lane & 7) + 8 * ((lane >> 3) & 1)) * LDB + n0 + 8 * (lane >> 4)) * 2)
                                : B + (uint32_t)(((n0 + (lane & 7) + 8 * (lane >> 4)) * LDB + 8 * ((lane >> 3) & 1)) * 2);
-#pragma unroll 2
-    for (int k = k0; k < k1; k += 16) {
-        uint32_t a[4];
+    // optional hand pipelining (-DGDKVM_BWD_PIPE: the fragment loads of k-step s + 1 issued before the MMAs of step s, two
+    // static register sets; ncu shows 35 % short-scoreboard stalls on the load -> mma dependency) -- off: it spills
+    uint32_t a0[4], a1[4], b0[NT / 2][4], b1[NT / 2][4];
+    auto load = [&](int k, uint32_t (&a)[4], uint32_t (&b)[NT / 2][4]) {
         if (TA) ldsm4t(a, a_lane + (uint32_t)(k * LDA * 2)); else ldsm4(a, a_lane + (uint32_t)(k * 2));
 #pragma unroll
         for (int nt = 0; nt < NT; nt += 2) {
-            uint32_t b[4];
-            if (TB) ldsm4t(b, b_lane + (uint32_t)((k * LDB + nt * 8) * 2)); else ldsm4(b, b_lane + (uint32_t)((nt * 8 * LDB + k) * 2));
-            mma16816(acc[nt], a, b[0], b[1]);
-            mma16816(acc[nt + 1], a, b[2], b[3]);
+            if (TB) ldsm4t(b[nt / 2], b_lane + (uint32_t)((k * LDB + nt * 8) * 2)); else ldsm4(b[nt / 2], b_lane + (uint32_t)((nt * 8 * LDB + k) * 2));
         }
+    };
+    auto mmas = [&](const uint32_t (&a)[4], const uint32_t (&b)[NT / 2][4]) {
+#pragma unroll
+        for (int nt = 0; nt < NT; nt += 2) {
+            mma16816(acc[nt], a, b[nt / 2][0], b[nt / 2][1]);
+            mma16816(acc[nt + 1], a, b[nt / 2][2], b[nt / 2][3]);
+        }
+    };
+    if (k0 >= k1) return;
+#ifdef GDKVM_BWD_PIPE        // measured: 13.6 ms against 10.8 ms without -- the second fragment set spills (280 bytes) at 128 registers
+    constexpr bool kPipe = NT <= 2;
+#else
+    constexpr bool kPipe = false;
+#endif
+    if constexpr (!kPipe) {            // NT = 4: four independent MMAs per A fragment already; a second register set would spill
+#pragma unroll 1
+        for (int k = k0; k < k1; k += 16) {
+            load(k, a0, b0);
+            mmas(a0, b0);
+        }
+        return;
+    }
+    load(k0, a0, b0);
+#pragma unroll 1
+    for (int k = k0; k < k1; k += 32) {
+        const bool more = k + 16 < k1;
+        if (more) load(k + 16, a1, b1);
+        mmas(a0, b0);
+        if (more) {
+            if (k + 32 < k1) load(k + 32, a0, b0);
+            mmas(a1, b1);
+        }
+    }
+}
+
+// Two 16 x 16 products that share their A operand (same rows, same k range): acc1 += A B1, acc2 += A B2.  One A fragment
+// feeds four independent MMAs per k-step instead of two (the 16 x 16 products are bound by the latency of their accumulate chains).
+template <bool TB1, bool TB2, int LDA, int LDB1, int LDB2>
+__device__ __forceinline__ void wgemm_pair(float (&acc1)[2][4], float (&acc2)[2][4], uint32_t A, int m0, uint32_t B1, uint32_t B2, int n0,
+                                           int k0, int k1, int lane) {
+    const uint32_t a_lane = A + (uint32_t)(((m0 + (lane & 15)) * LDA + 8 * (lane >> 4)) * 2);
+    const uint32_t b1_lane = TB1 ? B1 + (uint32_t)((((lane & 7) + 8 * ((lane >> 3) & 1)) * LDB1 + n0 + 8 * (lane >> 4)) * 2)
+                                 : B1 + (uint32_t)(((n0 + (lane & 7) + 8 * (lane >> 4)) * LDB1 + 8 * ((lane >> 3) & 1)) * 2);
+    const uint32_t b2_lane = TB2 ? B2 + (uint32_t)((((lane & 7) + 8 * ((lane >> 3) & 1)) * LDB2 + n0 + 8 * (lane >> 4)) * 2)
+                                 : B2 + (uint32_t)(((n0 + (lane & 7) + 8 * (lane >> 4)) * LDB2 + 8 * ((lane >> 3) & 1)) * 2);
+#pragma unroll 1
+    for (int k = k0; k < k1; k += 16) {
+        uint32_t a[4], b1[4], b2[4];
+        ldsm4(a, a_lane + (uint32_t)(k * 2));
+        if (TB1) ldsm4t(b1, b1_lane + (uint32_t)(k * LDB1 * 2)); else ldsm4(b1, b1_lane + (uint32_t)(k * 2));
+        if (TB2) ldsm4t(b2, b2_lane + (uint32_t)(k * LDB2 * 2)); else ldsm4(b2, b2_lane + (uint32_t)(k * 2));
+        mma16816(acc1[0], a, b1[0], b1[1]);
+        mma16816(acc2[0], a, b2[0], b2[1]);
+        mma16816(acc1[1], a, b1[2], b1[3]);
+        mma16816(acc2[1], a, b2[2], b2[3]);
     }
 }
 
@@ -144,21 +198,39 @@ __device__ __forceinline__ float col_sum(float x) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit_wait() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // rows [0, valid) x `cols` bf16 columns of a global tile (row stride in elements) -> padded shared tile; rows >= valid zero
-template <int LD>
+template <int LD, int COLS>
 __device__ __forceinline__ void load_tile(uint8_t* smem, uint32_t saddr, const __nv_bfloat16* src, int64_t row_stride, int rows, int valid,
-                                          int cols, int tid) {
-    const int cpr = cols >> 3;                       // 16-byte chunks per row
+                                          int tid) {
+    constexpr int cpr = COLS >> 3;                   // 16-byte chunks per row (a power of two: shifts, no division)
+#pragma unroll 2
     for (int idx = tid; idx < rows * cpr; idx += kBwdThreads) {
         const int r = idx / cpr, c = idx - r * cpr;
         if (r < valid) cp_async16(saddr + (uint32_t)((r * LD + c * 8) * 2), src + (int64_t)r * row_stride + c * 8);
         else *reinterpret_cast<uint4*>(smem + (r * LD + c * 8) * 2) = make_uint4(0u, 0u, 0u, 0u);
     }
 }
+
+// ---- optional phase timers (-DGDKVM_BWD_TIMERS, scripts/bwd_phase_timers.py): cycles of CTA 0 between consecutive barriers ----
+#ifdef GDKVM_BWD_TIMERS
+__device__ unsigned long long g_bwd_cycles[64];
+#define BT_DECL long long bt_prev = clock64();
+#define BT(slot)                                                                  \
+    do {                                                                          \
+        if (blockIdx.x == 0 && threadIdx.x == 0) {                                \
+            const long long bt_now = clock64();                                   \
+            g_bwd_cycles[slot] += (unsigned long long)(bt_now - bt_prev);         \
+            bt_prev = bt_now;                                                     \
+        }                                                                         \
+    } while (0)
+#else
+#define BT_DECL
+#define BT(slot) do { } while (0)
+#endif
+#define SYNC(slot) do { __syncthreads(); BT(slot); } while (0)
 
 template <int NH>
 __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrBwdParams p) {
@@ -169,9 +241,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
     float* sE = sGam + 64;                               // exp(Gamma_i)
     float* sBt = sE + 64;                                // beta_i
     float* sKd = sBt + 64;                               // gamma / e_i = exp(Gamma_last - Gamma_i)
-    float* sdGam = sKd + 64;                             // dGamma_i accumulators
-    float* sdBt = sdGam + 64;                            // dbeta_i accumulators
-    float* sMisc = sdBt + 64;                            // [0] sum_i (gamma / e_i) (dKh_i . k_i)   [1] <dS', S>
+    // Row / column sums of the chunk's products feed dGamma and dbeta.  Every partial sum has exactly ONE owner thread --
+    // row i, warp column wn: lane (g = i % 8.., t = 0) of warp (i / 16, wn); column j, warp row wm likewise -- so the owners
+    // accumulate with plain read-modify-writes (no shared-memory atomics: 128 of them on one address cost thousands of cycles
+    // per chunk), and one warp adds the four partials per row at the end of the chunk.
+    float* sRowG = sKd + 64;                             // [64 rows][4 warp columns]  dGamma, row-type terms
+    float* sRowB = sRowG + 256;                          // [64 rows][4 warp columns]  dbeta
+    float* sColG = sRowB + 256;                          // [64 columns][4 warp rows]  dGamma, column-type terms
+    float* sLast = sColG + 256;                          // [16 warps]                 terms of dGamma_last
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int wm = warp & 3, wn = warp >> 2, m0 = 16 * wm, n64 = 16 * wn, n128 = 32 * wn;
@@ -222,15 +299,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
             dS[hh][nt][0] = lo.x; dS[hh][nt][1] = lo.y; dS[hh][nt][2] = hi.x; dS[hh][nt][3] = hi.y;
         }
 
+    // K, Q and the first value half (V, dO, chunk-start state) of chunk cc -> K | Q buffer `par`, V / dO / S tiles
+    auto issue_chunk_loads = [&](int cc, int par) {
+        const int tt = cc << 6, vld = min(64, T - tt);
+        const uint32_t ok = oKQ + (uint32_t)par * 2 * SZ64;
+        load_tile<LD64, 64>(smem + ok, sb + ok, kg + (int64_t)tt * p.k_stride[1], p.k_stride[1], 64, vld, tid);
+        load_tile<LD64, 64>(smem + ok + SZ64, sb + ok + SZ64, qg + (int64_t)tt * p.q_stride[1], p.q_stride[1], 64, vld, tid);
+        load_tile<LD128, 128>(smem + oV, sb + oV, vg + (int64_t)tt * p.v_stride[1], p.v_stride[1], 64, vld, tid);
+        load_tile<LD128, 128>(smem + odO, sb + odO, dog + (int64_t)tt * p.do_stride[1], p.do_stride[1], 64, vld, tid);
+        load_tile<LD64, 64>(smem + oS, sb + oS, sg + (cs_blk0 + (int64_t)cc * cs_blk_stride) * V * 64, 64, 128, min(128, V), tid);
+        cp_async_commit();
+    };
+    if (NC > 0) issue_chunk_loads(NC - 1, 0);
+
+    BT_DECL
     for (int c = NC - 1; c >= 0; --c) {
         const int t0 = c << 6, valid = min(64, T - t0);
-        // ---- loads: K, Q and the first value half (V, dO, chunk-start state) ----
-        load_tile<LD64>(smem + oK, sb + oK, kg + (int64_t)t0 * p.k_stride[1], p.k_stride[1], 64, valid, 64, tid);
-        load_tile<LD64>(smem + oQ, sb + oQ, qg + (int64_t)t0 * p.q_stride[1], p.q_stride[1], 64, valid, 64, tid);
-        load_tile<LD128>(smem + oV, sb + oV, vg + (int64_t)t0 * p.v_stride[1], p.v_stride[1], 64, valid, 128, tid);
-        load_tile<LD128>(smem + odO, sb + odO, dog + (int64_t)t0 * p.do_stride[1], p.do_stride[1], 64, valid, 128, tid);
+        const int par = (NC - 1 - c) & 1;
+        const uint32_t oK = oKQ + (uint32_t)par * 2 * SZ64, oQ = oK + SZ64;
         const __nv_bfloat16* sc_ptr = sg + (cs_blk0 + (int64_t)c * cs_blk_stride) * V * 64;       // chunk-start state [V][64]
-        load_tile<LD64>(smem + oS, sb + oS, sc_ptr, 64, 128, min(128, V), 64, tid);
         if (warp == 0) {        // gates of the chunk: lane l holds tokens 2l, 2l + 1; pad tokens g = 0, beta = 0 (exact no-ops)
             float gv[2], bv[2];
 #pragma unroll
@@ -253,12 +340,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
             *reinterpret_cast<float2*>(sE + 2 * lane) = make_float2(__expf(G0), __expf(G1));
             *reinterpret_cast<float2*>(sBt + 2 * lane) = make_float2(bv[0], bv[1]);
             *reinterpret_cast<float2*>(sKd + 2 * lane) = make_float2(__expf(Gl - G0), __expf(Gl - G1));
-        } else if (warp == 1) {
-            sdGam[lane] = 0.f; sdGam[lane + 32] = 0.f; sdBt[lane] = 0.f; sdBt[lane + 32] = 0.f;
-            if (lane < 8) sMisc[lane] = 0.f;
+        } else {
+            for (int i = tid - 32; i < 3 * 256 + 16; i += kBwdThreads - 32) sRowG[i] = 0.f;
         }
-        cp_async_commit_wait();
-        __syncthreads();
+        cp_async_wait_all();
+        SYNC(0);
         const float gamma = sE[63];
 
         // ---- K K^T, Q K^T -> A (fp16, the solve's layout), K K^T D (bf16), P' = scale tril(Q K^T D) (bf16); Qe = scale e Q ----
@@ -300,12 +386,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
                 *reinterpret_cast<uint4*>(smem + oQe + (r * LD64 + ch * 8) * 2) = make_uint4(sc(x.x), sc(x.y), sc(x.z), sc(x.w));
             }
         }
-        __syncthreads();
+        SYNC(1);
         // ---- T = (I + A)^-1 (fp16, in place in H) ----
         if (warp < 2) tri::solve_levels01(smem + oH, sb + oH, warp, lane);
-        __syncthreads();
+        SYNC(2);
         if (warp < 4) tri::solve_level2(sb + oH, warp, lane, 5);
-        __syncthreads();
+        SYNC(3);
         {   // H -> T, Tb = T diag(beta), Tbe = T diag(beta e) as bf16 row-major tiles: thread = (row, 16-byte chunk)
             const int r = tid >> 3, ch = tid & 7;
             const uint4 hx = *reinterpret_cast<const uint4*>(smem + oH + sw128_offset(r, ch));
@@ -324,14 +410,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
             *reinterpret_cast<uint4*>(smem + oTb + (r * LD64 + ch * 8) * 2) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
             *reinterpret_cast<uint4*>(smem + oTbe + (r * LD64 + ch * 8) * 2) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
         }
-        __syncthreads();
+        SYNC(4);
         {   // Wn = -W = -Tbe K   (T is lower triangular: k < m0 + 16)
             float w[2][4];
             zero_acc(w);
             wgemm<2, false, true, LD64, LD64>(w, sb + oTbe, m0, sb + oK, n64, 0, m0 + 16, lane);
             store_tile<2, LD64>(smem + oWn, w, m0, n64, lane, -1.f);
         }
-        __syncthreads();
+        SYNC(5);
 
         // partial results of the chunk that are sums over the value dimension (kept in registers across the halves)
         float dP[2][4], G2[2][4], dQS[2][4], dWa[2][4], dKh[2][4];
@@ -339,29 +425,38 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
 
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh) {
-            if (hh > 0) {        // second value half through the same tiles
-                load_tile<LD128>(smem + oV, sb + oV, vg + (int64_t)t0 * p.v_stride[1] + 128, p.v_stride[1], 64, valid, 128, tid);
-                load_tile<LD128>(smem + odO, sb + odO, dog + (int64_t)t0 * p.do_stride[1] + 128, p.do_stride[1], 64, valid, 128, tid);
-                load_tile<LD64>(smem + oS, sb + oS, sc_ptr + 128 * 64, 64, 128, 128, 64, tid);
-                cp_async_commit_wait();
-                __syncthreads();
+            if (hh > 0) {        // second value half through the same tiles (issued while the first half's dV left)
+                cp_async_wait_all();
+                SYNC(6 + 24 * hh);
             }
-            {   // bf16 copy of dS' (this half) as an MMA operand; <dS', S> for the gate gradient
+            {   // bf16 copy of dS' (this half) as an MMA operand; <dS', S> for the gate gradient (S [value][key dim] read with
+                // ldmatrix.trans, which delivers exactly the accumulator layout: lane (g, t) <-> key dim g, values 2t, 2t + 1)
                 float acc = 0.f;
+#pragma unroll
+                for (int nt = 0; nt < 4; nt += 2) {
+                    uint32_t sf[4];
+                    ldsm4t(sf, sb + oS + (uint32_t)(((n128 + (nt + (lane >> 4)) * 8 + (lane & 7)) * LD64 + m0 + 8 * ((lane >> 3) & 1)) * 2));
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int r8 = 0; r8 < 2; ++r8) {
+                            const uint32_t w = sf[2 * u + r8];
+                            acc = fmaf(dS[hh][nt + u][2 * r8], __uint_as_float(w << 16), acc);
+                            acc = fmaf(dS[hh][nt + u][2 * r8 + 1], __uint_as_float(w & 0xffff0000u), acc);
+                        }
+                }
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                     for (int r8 = 0; r8 < 2; ++r8) {
                         const int kd = m0 + g + 8 * r8, vc = n128 + nt * 8 + 2 * t;
                         *reinterpret_cast<uint32_t*>(smem + odSb + (kd * LD128 + vc) * 2) = pack_bf16(dS[hh][nt][2 * r8], dS[hh][nt][2 * r8 + 1]);
-                        const __nv_bfloat16* sp = reinterpret_cast<const __nv_bfloat16*>(smem + oS);
-                        acc += dS[hh][nt][2 * r8] * __bfloat162float(sp[vc * LD64 + kd]) + dS[hh][nt][2 * r8 + 1] * __bfloat162float(sp[(vc + 1) * LD64 + kd]);
                     }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-                if (lane == 0) atomicAdd(&sMisc[1], acc);
+                if (lane == 0) sLast[warp] += gamma * acc;
             }
-            __syncthreads();
+            SYNC(7 + 24 * hh);
             {   // Vn = Tb V + Wn S  (rows i = m0.., columns n128..)
                 float a[4][4];
                 zero_acc(a);
@@ -379,7 +474,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
                 wgemm<4, true, true, LD64, LD128>(a, sb + oP, m0, sb + odO, n128, m0, 64, lane);
                 store_tile<4, LD128>(smem + odVn, a, m0, n128, lane);
             }
-            __syncthreads();
+            SYNC(8 + 24 * hh);
             // dS = gamma dS' + Qe^T dO + Wn^T dVn
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
@@ -387,16 +482,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
                 for (int e = 0; e < 4; ++e) dS[hh][nt][e] *= gamma;
             wgemm<4, true, true, LD64, LD128>(dS[hh], sb + oQe, m0, sb + odO, n128, 0, 64, lane);
             wgemm<4, true, true, LD64, LD128>(dS[hh], sb + oWn, m0, sb + odVn, n128, 0, 64, lane);
-            if (wn <= wm) {      // lower-triangular outputs
-                wgemm<2, false, false, LD128, LD128>(dP, sb + odO, m0, sb + oVn, n64, 0, 128, lane);     // dP' += dO Vn^T
-                wgemm<2, false, false, LD128, LD128>(G2, sb + odVn, m0, sb + oV, n64, 0, 128, lane);     // G2  += dVn V^T
+            if (wn <= wm) {      // lower-triangular outputs too: products that share an A operand go in pairs
+                wgemm_pair<false, true, LD128, LD128, LD64>(dP, dQS, sb + odO, m0, sb + oVn, sb + oS, n64, 0, 128, lane);     // dP' += dO Vn^T, dO S^T
+                wgemm_pair<false, true, LD128, LD128, LD64>(G2, dWa, sb + odVn, m0, sb + oV, sb + oS, n64, 0, 128, lane);     // G2 += dVn V^T, dVn S^T (= -dW)
+            } else {
+                wgemm<2, false, true, LD128, LD64>(dQS, sb + odO, m0, sb + oS, n64, 0, 128, lane);           // dO S^T
+                wgemm<2, false, true, LD128, LD64>(dWa, sb + odVn, m0, sb + oS, n64, 0, 128, lane);          // dVn S^T  (= -dW)
             }
-            wgemm<2, false, true, LD128, LD64>(dQS, sb + odO, m0, sb + oS, n64, 0, 128, lane);           // dO S^T
-            wgemm<2, false, true, LD128, LD64>(dWa, sb + odVn, m0, sb + oS, n64, 0, 128, lane);          // dVn S^T  (= -dW)
             wgemm<2, false, false, LD128, LD128>(dKh, sb + oVn, m0, sb + odSb, n64, 0, 128, lane);       // Vn dS'^T
-            __syncthreads();
-            {   // dV = diag(beta) T^T dVn, written over V in place (each thread reads exactly the V elements it overwrites);
-                // dbeta_j += (T^T dVn)_j . v_j
+            {   // dV = diag(beta) T^T dVn -> staging tile;  dbeta_j += (T^T dVn)_j . v_j
                 float a[4][4];
                 zero_acc(a);
                 wgemm<4, true, true, LD64, LD128>(a, sb + oT, m0, sb + odVn, n128, m0, 64, lane);
@@ -408,23 +502,31 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
                     const float2 v0 = bf2(smem + oV, m0 + g, vc, LD128), v1 = bf2(smem + oV, m0 + g + 8, vc, LD128);
                     d0 += a[nt][0] * v0.x + a[nt][1] * v0.y;
                     d1 += a[nt][2] * v1.x + a[nt][3] * v1.y;
-                    *reinterpret_cast<uint32_t*>(smem + oV + ((m0 + g) * LD128 + vc) * 2) = pack_bf16(a[nt][0] * b0, a[nt][1] * b0);
-                    *reinterpret_cast<uint32_t*>(smem + oV + ((m0 + g + 8) * LD128 + vc) * 2) = pack_bf16(a[nt][2] * b1, a[nt][3] * b1);
+                    *reinterpret_cast<uint32_t*>(smem + odVst + ((m0 + g) * LD128 + vc) * 2) = pack_bf16(a[nt][0] * b0, a[nt][1] * b0);
+                    *reinterpret_cast<uint32_t*>(smem + odVst + ((m0 + g + 8) * LD128 + vc) * 2) = pack_bf16(a[nt][2] * b1, a[nt][3] * b1);
                 }
                 d0 = quad_sum(d0); d1 = quad_sum(d1);
-                if (t == 0) { atomicAdd(&sdBt[m0 + g], d0); atomicAdd(&sdBt[m0 + g + 8], d1); }
+                if (t == 0) { sRowB[(m0 + g) * 4 + wn] += d0; sRowB[(m0 + g + 8) * 4 + wn] += d1; }
             }
-            __syncthreads();
+            SYNC(9 + 24 * hh);
+            // V, dO, S are free: fetch the next value half -- or, behind the last one, the next chunk -- while dV leaves
+            if (hh + 1 < NH) {
+                load_tile<LD128, 128>(smem + oV, sb + oV, vg + (int64_t)t0 * p.v_stride[1] + (hh + 1) * 128, p.v_stride[1], 64, valid, tid);
+                load_tile<LD128, 128>(smem + odO, sb + odO, dog + (int64_t)t0 * p.do_stride[1] + (hh + 1) * 128, p.do_stride[1], 64, valid, tid);
+                load_tile<LD64, 64>(smem + oS, sb + oS, sc_ptr + (hh + 1) * 128 * 64, 64, 128, 128, tid);
+                cp_async_commit();
+            } else if (c > 0) {
+                issue_chunk_loads(c - 1, par ^ 1);
+            }
             {   // dV half -> global (16-byte stores, valid rows only)
                 const int cols = min(128, V - hh * 128) >> 3;
                 for (int idx = tid; idx < 64 * 16; idx += kBwdThreads) {
                     const int r = idx >> 4, ch = idx & 15;
                     if (r < valid && ch < cols)
                         *reinterpret_cast<uint4*>(dvg + (int64_t)(t0 + r) * p.dv_stride[1] + hh * 128 + ch * 8) =
-                            *reinterpret_cast<const uint4*>(smem + oV + (r * LD128 + ch * 8) * 2);
+                            *reinterpret_cast<const uint4*>(smem + odVst + (r * LD128 + ch * 8) * 2);
                 }
             }
-            __syncthreads();
         }
 
         // ---- tail: the 64 x 64 quantities ----
@@ -447,14 +549,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
                     *reinterpret_cast<uint32_t*>(smem + odPD + (i * LD64 + j) * 2) = pack_bf16(scale * dP[nt][2 * r8] * d0, scale * dP[nt][2 * r8 + 1] * d1);
                 }
                 cs0 = col_sum(cs0); cs1 = col_sum(cs1);
-                if (g == 0) { atomicAdd(&sdGam[j], -cs0); atomicAdd(&sdGam[j + 1], -cs1); }
+                if (g == 0) { sColG[j * 4 + wm] -= cs0; sColG[(j + 1) * 4 + wm] -= cs1; }
             }
             rs0 = quad_sum(rs0); rs1 = quad_sum(rs1);
-            if (t == 0) { atomicAdd(&sdGam[m0 + g], rs0); atomicAdd(&sdGam[m0 + g + 8], rs1); }
+            if (t == 0) { sRowG[(m0 + g) * 4 + wn] += rs0; sRowG[(m0 + g + 8) * 4 + wn] += rs1; }
         } else {
             zero_tile16<LD64>(smem + odPD, m0, n64, lane);
         }
-        __syncthreads();
+        SYNC(10);
         float accK[2][4];
         {   // dQ = scale e (dO S^T) + dPD K;  dGamma_i += scale e_i q_i . (dO S^T)_i
             const float f0 = scale * sE[m0 + g], f1 = scale * sE[m0 + g + 8];
@@ -468,7 +570,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
                 dQS[nt][0] *= f0; dQS[nt][1] *= f0; dQS[nt][2] *= f1; dQS[nt][3] *= f1;
             }
             d0 = quad_sum(d0); d1 = quad_sum(d1);
-            if (t == 0) { atomicAdd(&sdGam[m0 + g], f0 * d0); atomicAdd(&sdGam[m0 + g + 8], f1 * d1); }
+            if (t == 0) { sRowG[(m0 + g) * 4 + wn] += f0 * d0; sRowG[(m0 + g + 8) * 4 + wn] += f1 * d1; }
             wgemm<2, false, true, LD64, LD64>(dQS, sb + odPD, m0, sb + oK, n64, 0, m0 + 16, lane);
             store_tile<2, LD64>(smem + oOutQ, dQS, m0, n64, lane);
         }
@@ -491,9 +593,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
             const float e0 = sE[m0 + g], e1 = sE[m0 + g + 8], b0 = sBt[m0 + g], b1 = sBt[m0 + g + 8];
             const float kd0 = sKd[m0 + g], kd1 = sKd[m0 + g + 8];
             if (t == 0) {
-                atomicAdd(&sdBt[m0 + g], e0 * d0); atomicAdd(&sdBt[m0 + g + 8], e1 * d1);
-                atomicAdd(&sdGam[m0 + g], b0 * e0 * d0 - kd0 * h0); atomicAdd(&sdGam[m0 + g + 8], b1 * e1 * d1 - kd1 * h1);
-                atomicAdd(&sMisc[0], kd0 * h0 + kd1 * h1);
+                sRowB[(m0 + g) * 4 + wn] += e0 * d0; sRowB[(m0 + g + 8) * 4 + wn] += e1 * d1;
+                sRowG[(m0 + g) * 4 + wn] += b0 * e0 * d0 - kd0 * h0; sRowG[(m0 + g + 8) * 4 + wn] += b1 * e1 * d1 - kd1 * h1;
+            }
+            {   // sum_i (gamma / e_i) (dKh_i . k_i) of this warp's rows goes to dGamma_last (h0, h1 are quad sums: lanes t = 0 hold them)
+                float hl = t == 0 ? kd0 * h0 + kd1 * h1 : 0.f;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) hl += __shfl_xor_sync(0xffffffffu, hl, off);
+                if (lane == 0) sLast[warp] += hl;
             }
 #pragma unroll
             for (int nt = 0; nt < 2; ++nt) {
@@ -517,7 +624,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
         } else {
             zero_tile16<LD64>(smem + odT, m0, n64, lane);
         }
-        __syncthreads();
+        SYNC(11);
         if (wn <= wm) {   // X = T^T dT (lower part)
             float x[2][4];
             zero_acc(x);
@@ -526,7 +633,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
         } else {
             zero_tile16<LD64>(smem + oX, m0, n64, lane);
         }
-        __syncthreads();
+        SYNC(12);
         if (wn <= wm) {   // dA = -X T^T (strictly lower);  M = dA diag_rows(beta) D;  dbeta, dGamma from dA . (K K^T D)
             float a[2][4];
             zero_acc(a);
@@ -549,23 +656,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
                     *reinterpret_cast<uint32_t*>(smem + oM + (i * LD64 + j) * 2) = pack_bf16(a0 * bi * d0, a1 * bi * d1);
                 }
                 cs0 = col_sum(cs0); cs1 = col_sum(cs1);
-                if (g == 0) { atomicAdd(&sdGam[j], -cs0); atomicAdd(&sdGam[j + 1], -cs1); }
+                if (g == 0) { sColG[j * 4 + wm] -= cs0; sColG[(j + 1) * 4 + wm] -= cs1; }
             }
             rs0 = quad_sum(rs0); rs1 = quad_sum(rs1);
             if (t == 0) {
-                atomicAdd(&sdBt[m0 + g], rs0); atomicAdd(&sdBt[m0 + g + 8], rs1);
-                atomicAdd(&sdGam[m0 + g], sBt[m0 + g] * rs0); atomicAdd(&sdGam[m0 + g + 8], sBt[m0 + g + 8] * rs1);
+                sRowB[(m0 + g) * 4 + wn] += rs0; sRowB[(m0 + g + 8) * 4 + wn] += rs1;
+                sRowG[(m0 + g) * 4 + wn] += sBt[m0 + g] * rs0; sRowG[(m0 + g + 8) * 4 + wn] += sBt[m0 + g + 8] * rs1;
             }
         } else {
             zero_tile16<LD64>(smem + oM, m0, n64, lane);
         }
-        __syncthreads();
+        SYNC(13);
         // dK = diag(gamma / e) dKh + diag(beta e) dBt (accK) + dPD^T Q + M K + M^T K
         wgemm<2, true, true, LD64, LD64>(accK, sb + odPD, m0, sb + oQ, n64, m0, 64, lane);
         wgemm<2, false, true, LD64, LD64>(accK, sb + oM, m0, sb + oK, n64, 0, m0 + 16, lane);
         wgemm<2, true, true, LD64, LD64>(accK, sb + oM, m0, sb + oK, n64, m0, 64, lane);
         store_tile<2, LD64>(smem + oOutK, accK, m0, n64, lane);
-        __syncthreads();
+        SYNC(14);
         {   // dq, dk tiles -> global; dg = reverse cumsum of dGamma; dbeta
             const int r = tid >> 3, ch = tid & 7;
             if (r < valid) {
@@ -573,8 +680,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
                 *reinterpret_cast<uint4*>(dkg + (int64_t)(t0 + r) * p.dk_stride[1] + ch * 8) = *reinterpret_cast<const uint4*>(smem + oOutK + (r * LD64 + ch * 8) * 2);
             }
             if (warp == 0) {
-                float x0 = sdGam[2 * lane], x1 = sdGam[2 * lane + 1];
-                if (lane == 31) x1 += sMisc[0] + gamma * sMisc[1];       // terms of Gamma_last: K-hat and gamma S
+                const float4 ra = *reinterpret_cast<const float4*>(sRowG + 8 * lane), rb = *reinterpret_cast<const float4*>(sRowG + 8 * lane + 4);
+                const float4 ca = *reinterpret_cast<const float4*>(sColG + 8 * lane), cb = *reinterpret_cast<const float4*>(sColG + 8 * lane + 4);
+                const float4 ba = *reinterpret_cast<const float4*>(sRowB + 8 * lane), bb = *reinterpret_cast<const float4*>(sRowB + 8 * lane + 4);
+                float x0 = (ra.x + ra.y) + (ra.z + ra.w) + (ca.x + ca.y) + (ca.z + ca.w);
+                float x1 = (rb.x + rb.y) + (rb.z + rb.w) + (cb.x + cb.y) + (cb.z + cb.w);
+                const float db0 = (ba.x + ba.y) + (ba.z + ba.w), db1 = (bb.x + bb.y) + (bb.z + bb.w);
+                {   // terms of Gamma_last (K-hat and gamma S): the sixteen per-warp sums
+                    float l = lane < 16 ? sLast[lane] : 0.f;
+#pragma unroll
+                    for (int off = 8; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+                    l = __shfl_sync(0xffffffffu, l, 0);
+                    if (lane == 31) x1 += l;
+                }
                 float s = x0 + x1;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
@@ -582,11 +700,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
                     if (lane + off < 32) s += u;
                 }
                 const int64_t o0 = ((int64_t)b * p.T + tok0 + t0 + 2 * lane) * p.H + h;
-                if (2 * lane < valid) { p.dg[o0] = s; p.dbeta[o0] = sdBt[2 * lane]; }
-                if (2 * lane + 1 < valid) { p.dg[o0 + p.H] = s - x0; p.dbeta[o0 + p.H] = sdBt[2 * lane + 1]; }
+                if (2 * lane < valid) { p.dg[o0] = s; p.dbeta[o0] = db0; }
+                if (2 * lane + 1 < valid) { p.dg[o0 + p.H] = s - x0; p.dbeta[o0 + p.H] = db1; }
             }
         }
-        __syncthreads();
+        SYNC(15);
     }
 
     if (p.d_initial_state != nullptr) {
@@ -642,3 +760,15 @@ int launch_bwd(const GdkvmGdrBwdParams& p, cudaStream_t stream) {
 }
 
 }  // namespace gdkvm
+
+#ifdef GDKVM_BWD_TIMERS
+extern "C" int gdkvm_debug_bwd_cycles(unsigned long long* out, int n) {
+    unsigned long long h[64];
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(h, gdkvm::g_bwd_cycles, sizeof h) != cudaSuccess) return -1;
+    for (int i = 0; i < n && i < 64; ++i) out[i] = h[i];
+    unsigned long long z[64] = {0};
+    cudaMemcpyToSymbol(gdkvm::g_bwd_cycles, z, sizeof z);
+    return 0;
+}
+#endif
