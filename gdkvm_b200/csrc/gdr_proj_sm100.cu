@@ -11,11 +11,10 @@
 // GEMM -> y in HBM -> two normalisation passes -> elementwise gate kernels) this removes one full write + read of y.
 //
 // Persistent: one CTA per SM takes 128-token row blocks; the block's feature tile (128 x D bf16, up to 128 KB) is loaded ONCE
-// and stays in shared memory while the CTA walks all N / 128 column tiles of the block, so each output tile costs one 128 x D
-// weight tile from L2 (the 1.6 MB weight stays L2-resident) instead of a feature tile and a weight tile.  With D <= 256 the
-// feature tile is double-buffered (the next block's lands under the current block's last tiles).  6 warps: TMA producer
-// (feature block + a 4-stage ring of 16 KB weight k-blocks), MMA issuer (two 128-column TMEM accumulators, so the MMAs of
-// tile i + 1 overlap the epilogue of tile i), four epilogue warps (one per TMEM lane quarter) that transpose their rows through
+// and stays in shared memory while the CTA walks all N / 256 column tiles of the block, so each output tile costs one 256 x D
+// weight tile from L2 (the 1.6 MB weight stays L2-resident) instead of a feature tile and a weight tile.  10 warps: TMA producer
+// (feature block + a ring of 32 KB weight k-blocks, four stages deep at D <= 256), MMA issuer (two 256-column TMEM accumulators, so the MMAs of
+// tile i + 1 overlap the epilogue of tile i), eight epilogue warps (two per TMEM lane quarter, two of a tile's four 64-column groups each) that transpose their rows through
 // a swizzled shared-memory staging tile so that every global store instruction writes whole 128-byte lines.
 // Bound: HBM writes (772 B per token-head against 2 D bytes read per token).
 #include <algorithm>
@@ -30,13 +29,18 @@ namespace {
 
 using namespace sm100;
 
-constexpr int kProjThreads = 192;
-constexpr int kWStages = 4;
+constexpr int kProjThreads = 320;                                               // producer, MMA issuer, eight epilogue warps
+constexpr int kMaxWStages = 4;
+constexpr int kBN = 256;                                                        // output columns per tile = N of one tcgen05.mma
 constexpr uint32_t kTileBytes = 128 * 64 * 2;                                   // 128 rows x 64 bf16 (one swizzle atom wide)
-constexpr uint32_t kOffW = 8 * kTileBytes;                                      // feature blocks: 2 x (D <= 256) or 1 x (D <= 512)
-constexpr uint32_t kOffStaging = kOffW + kWStages * kTileBytes;                 // 4 epilogue warps x 32 rows x 128 B
-constexpr uint32_t kOffProjBar = kOffStaging + 4 * 4096;
-constexpr uint32_t kProjSmem = kOffProjBar + 256 + 1024;                        // + barriers + alignment slack
+constexpr uint32_t kWTileBytes = kBN * 64 * 2;                                  // a weight k-block: 256 rows x 64 bf16
+// feature block (D / 64 tiles of 16 KB: 64 KB at D = 256, at most 128 KB) followed by the ring of 32 KB weight k-blocks: 192 KB
+// in all, so D <= 256 leaves four weight stages (128 KB in flight -- a k-block comes from L2, ~2 k cycles away) and D = 512 two.
+// N = 256 per MMA because ISSUING an MMA costs ~100 cycles on the one issuer warp: at N = 128 the
+// 64-cycle MMAs were issue-bound (0.92 ms).
+constexpr uint32_t kOffStaging = 12 * kTileBytes;                               // 8 epilogue warps x 32 rows x 128 B
+constexpr uint32_t kOffProjBar = kOffStaging + 8 * 4096;
+constexpr uint32_t kProjSmem = kOffProjBar + 512 + 1024;                        // + barriers + alignment slack
 static_assert(kProjSmem <= 232448, "exceeds the 227 KB dynamic shared memory limit");
 
 __device__ __forceinline__ float log_sigmoid(float x) { return fminf(x, 0.f) - log1pf(__expf(-fabsf(x))); }
@@ -48,9 +52,9 @@ qkvgb_proj_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sbase = smem_u32(smem);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffProjBar);
-    uint64_t* w_full = bars;                          // [kWStages] weight k-block landed (tx)
-    uint64_t* w_empty = bars + kWStages;              // [kWStages] its MMAs completed (commit)
-    uint64_t* a_full = bars + 2 * kWStages;           // [2] feature block landed (tx)
+    uint64_t* w_full = bars;                          // [stages] weight k-block landed (tx)
+    uint64_t* w_empty = bars + kMaxWStages;           // [stages] its MMAs completed (commit)
+    uint64_t* a_full = bars + 2 * kMaxWStages;        // [2] feature block landed (tx)
     uint64_t* a_empty = a_full + 2;                   // [2] every MMA of the row block completed (commit)
     uint64_t* acc_full = a_empty + 2;                 // [2] accumulators of a tile complete (commit)
     uint64_t* acc_empty = acc_full + 2;               // [2] accumulators drained by the four epilogue warps
@@ -58,15 +62,17 @@ qkvgb_proj_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int KB = p.D >> 6;
-    const uint32_t nbuf = KB <= 4 ? 2u : 1u;          // feature-block buffers (each KB x 16 KB)
+    const uint32_t nbuf = 1u;                         // feature-block buffers (one: the smem goes to the weight ring; the block's
+                                                      // reload is exposed once per n_tiles tiles)
     const uint32_t abytes = (uint32_t)KB * kTileBytes;
+    const uint32_t kOffW = abytes, kWStages = min((12u - (uint32_t)KB) / 2u, (uint32_t)kMaxWStages);
 
     if (tid == 0) {
-        for (int i = 0; i < kWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < kMaxWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(s_tmem, 256);
+    if (warp == 1) tmem_alloc(s_tmem, 512);
     if (warp == 0 && lane == 0) { tma_prefetch_desc(&mx); tma_prefetch_desc(&mw); }
     tc_fence_before_sync();
     __syncthreads();
@@ -89,16 +95,16 @@ qkvgb_proj_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
                     const uint32_t s = it % kWStages;
                     if (it >= kWStages) mbar_wait_inl(&w_empty[s], (it / kWStages - 1) & 1u);
                     if (elect_one()) {
-                        mbar_arrive_expect_tx(&w_full[s], kTileBytes);
-                        tma_load_2d(smem + kOffW + s * kTileBytes, &mw, &w_full[s], kb * 64, tn * 128);
+                        mbar_arrive_expect_tx(&w_full[s], kWTileBytes);
+                        tma_load_2d(smem + kOffW + s * kWTileBytes, &mw, &w_full[s], kb * 64, tn * kBN);
                     }
                     __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ---- MMA issuer: D[128 x 128] += X_block[:, kb] W_tile[128 x 64]^T, four K = 16 slices per weight k-block ----
-        constexpr uint32_t kIdesc = umma_idesc_bf16(128, 128, false, false);
+        // ---- MMA issuer: D[128 x 256] += X_block[:, kb] W_tile[256 x 64]^T, four K = 16 slices per weight k-block ----
+        constexpr uint32_t kIdesc = umma_idesc_bf16(128, kBN, false, false);
         uint32_t it = 0, i = 0, j = 0;
         for (int64_t tm = blockIdx.x; tm < m_tiles; tm += gridDim.x, ++j) {
             const uint32_t ab = j % nbuf;
@@ -112,8 +118,8 @@ qkvgb_proj_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
                     mbar_wait_inl(&w_full[s], (it / kWStages) & 1u);
                     tc_fence_after_sync();
                     const uint64_t da = umma_smem_desc_sw128(sbase + ab * abytes + (uint32_t)kb * kTileBytes, 16, 1024);
-                    const uint64_t db = umma_smem_desc_sw128(sbase + kOffW + s * kTileBytes, 16, 1024);
-                    umma4_ss_w(tmem + buf * 128, da, da + 2, da + 4, da + 6, db, db + 2, db + 4, db + 6, kIdesc, kb > 0);
+                    const uint64_t db = umma_smem_desc_sw128(sbase + kOffW + s * kWTileBytes, 16, 1024);
+                    umma4_ss_w(tmem + buf * kBN, da, da + 2, da + 4, da + 6, db, db + 2, db + 4, db + 6, kIdesc, kb > 0);
                     umma_commit_w(&w_empty[s]);
                 }
                 umma_commit_w(&acc_full[buf]);
@@ -121,8 +127,10 @@ qkvgb_proj_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
             umma_commit_w(&a_empty[ab]);           // the feature block may be overwritten once every MMA issued so far has completed
         }
     } else {
-        // ---- epilogue: one thread = one token row, 64 columns (one head of q / k, a quarter head of v, or the gates) at a time ----
-        const int quarter = warp & 3;
+        // ---- epilogue: one thread = one token row, 64 columns (one head of q / k, a quarter head of v, or the gates) of every tile.
+        // Eight warps: two per TMEM lane quarter, one for each 64-column half of the tile -- with a single epilogue warp per
+        // scheduler the load -> normalise -> stage -> store chain of a tile (~3.5 k cycles) outlasted its MMAs (~1 k) ----
+        const int quarter = warp & 3, gsel = (warp - 2) >> 2;
         uint8_t* stg = smem + kOffStaging + (warp - 2) * 4096;
         const int H = p.H, Nq = H * 64, Nv = H * p.V, Ntot = 2 * Nq + Nv + 2 * H;
         uint32_t i = 0;
@@ -130,19 +138,19 @@ qkvgb_proj_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
         for (int tn = 0; tn < n_tiles; ++tn, ++i) {
             const int64_t row0 = tm * 128 + quarter * 32;
             const uint32_t buf = i & 1u;
-            const uint32_t taddr = tmem + buf * 128 + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t taddr = tmem + buf * kBN + ((uint32_t)(quarter * 32) << 16);
             mbar_wait_inl(&acc_full[buf], (i / 2) & 1u);
             tc_fence_after_sync();
 #pragma unroll 1
-            for (int gi = 0; gi < 2; ++gi) {
-                const int col0 = tn * 128 + gi * 64;
+            for (int gi = 2 * gsel; gi < 2 * gsel + 2; ++gi) {
+                const int col0 = tn * kBN + gi * 64;
                 uint32_t r0[32], r1[32];
                 if (col0 < Ntot) {
                     tmem_ld32(taddr + gi * 64, r0);
                     tmem_ld32(taddr + gi * 64 + 32, r1);
                     tmem_wait_ld();
                 }
-                if (gi == 1) {         // every TMEM load of this tile has completed: hand the accumulator back to the MMA warp
+                if (gi == 2 * gsel + 1) {   // this warp's TMEM loads of the tile have completed: hand the accumulator back (8 arrivals)
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -218,7 +226,7 @@ qkvgb_proj_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem, 256);
+    if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
@@ -253,12 +261,12 @@ int launch_proj(const GdkvmProjParams& p, cudaStream_t stream) {
     {
         const uint64_t dx[2] = {(uint64_t)p.D, (uint64_t)p.R}, sx[1] = {(uint64_t)p.x_row_stride * 2};
         const uint64_t dw[2] = {(uint64_t)p.D, (uint64_t)N}, sw[1] = {(uint64_t)p.D * 2};
-        const uint32_t box[2] = {64, 128};                      // one 128-row, 64-column (128-byte) swizzle atom per TMA load
+        const uint32_t box[2] = {64, 128}, boxw[2] = {64, (uint32_t)kBN};     // 64 columns = one 128-byte swizzle atom per row
         int rc = make_tmap(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.x, dx, sx, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc == 0) rc = make_tmap(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.w, dw, sw, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc == 0) rc = make_tmap(&mw, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, p.w, dw, sw, boxw, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc != 0) return (int)cudaErrorInvalidValue;
     }
-    const int n_tiles = (int)((N + 127) / 128);
+    const int n_tiles = (int)((N + kBN - 1) / kBN);
     const int64_t m_tiles = (p.R + 127) / 128;
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) { (void)cudaGetLastError(); sms = 148; }
