@@ -22,6 +22,7 @@
 //
 // Bound: HBM in principle (algorithmic bytes per token-head: q,k,v,do read + dq,dk,dv written + chunk state read =
 // 2 576 + 512 B); this first version is bound by its own instruction issue and exposed load latency.
+#include <algorithm>
 #include <mutex>
 
 #include "gdr_common.cuh"
@@ -232,8 +233,13 @@ __device__ unsigned long long g_bwd_cycles[64];
 #endif
 #define SYNC(slot) do { __syncthreads(); BT(slot); } while (0)
 
+// Time segments (the forward kernel's scheme, mirrored in time): one CTA per chain leaves a ragged last wave (512 chains on
+// 148 SMs = 3.46 waves), so a chain may be cut at chunk boundaries into `nseg` segments that are separate work units taken in
+// ticket order; segment 0 is the LAST one in time (the reverse scan starts there) and hands its fp32 state cotangent to the
+// next unit of the chain through a per-launch scratch + release / acquire flag.  Arithmetic identical bit for bit.
 template <int NH>
-__global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrBwdParams p) {
+__global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrBwdParams p, const int nseg, const int seg_chunks,
+                                                                 float* __restrict__ xstate, int* __restrict__ xsync) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t sb = smem_u32(smem);
@@ -254,7 +260,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
     const int wm = warp & 3, wn = warp >> 2, m0 = 16 * wm, n64 = 16 * wn, n128 = 32 * wn;
     // batched: chain = (clip, head), tokens 0 .. T-1 of clip b.  Packed clips: chain = (sequence, head), rows cu[n] .. cu[n+1]-1
     // of the one packed clip; chunk-state slot of chunk c = cu[n] / 64 + n + c (gdkvm_gdr.h).
-    const int chain = blockIdx.x, V = p.V;
+    const int V = p.V;
+    int unit = blockIdx.x;
+    if (nseg > 1) {                      // ticket order: a unit's predecessor (same chain, previous segment) is resident or done
+        int* s_unit = reinterpret_cast<int*>(sLast + 16);
+        if (tid == 0) *s_unit = atomicAdd(xsync, 1);
+        __syncthreads();
+        unit = *s_unit;
+    }
+    const int nchains = (p.cu_seqlens != nullptr ? p.n_seqs : p.B) * p.H;
+    const int seg = unit / nchains, chain = unit - seg * nchains;
     int b = chain / p.H;
     const int h = chain - b * p.H;
     int T = p.T;
@@ -270,6 +285,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
     }
     const int NC = (T + 63) >> 6;
     const float scale = p.scale;
+    // chunks of this unit: time segment ts = nseg - 1 - seg covers chunks [c_lo, c_hi]
+    const int c_lo = nseg > 1 ? (nseg - 1 - seg) * seg_chunks : 0;
+    const int c_hi = (nseg > 1 ? min(NC, c_lo + seg_chunks) : NC) - 1;
 
     const __nv_bfloat16* qg = reinterpret_cast<const __nv_bfloat16*>(p.q) + (int64_t)b * p.q_stride[0] + (int64_t)h * p.q_stride[2] + tok0 * p.q_stride[1];
     const __nv_bfloat16* kg = reinterpret_cast<const __nv_bfloat16*>(p.k) + (int64_t)b * p.k_stride[0] + (int64_t)h * p.k_stride[2] + tok0 * p.k_stride[1];
@@ -285,16 +303,29 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
     // state cotangent dS [64 key dims x V], fp32, in registers: warp (wm, wn) owns rows 16 wm .. + 15, columns 32 wn .. + 31 of
     // each 128-column half
     float dS[NH][4][4];
+    const float* ds_src = p.d_final_state;
+    if (seg > 0) {                       // the later time segment of this chain publishes its dS in the scratch
+        if (tid == 0) {
+            const int* flag = xsync + 1 + chain;
+            uint32_t polls = 0;
+            while (sm100::ld_acquire_gpu(flag) < seg) {
+                __nanosleep(256);
+                if (++polls > (1u << 28)) __trap();
+            }
+        }
+        __syncthreads();
+        ds_src = xstate;
+    }
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh)
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
             const int col = hh * 128 + n128 + nt * 8 + 2 * t;
             float2 lo = make_float2(0.f, 0.f), hi = lo;
-            if (p.d_final_state != nullptr && col < V) {
-                const float* src = p.d_final_state + (int64_t)chain * 64 * V + col;
-                lo = *reinterpret_cast<const float2*>(src + (int64_t)(m0 + g) * V);
-                hi = *reinterpret_cast<const float2*>(src + (int64_t)(m0 + g + 8) * V);
+            if (ds_src != nullptr && col < V) {
+                const float* src = ds_src + (int64_t)chain * 64 * V + col;
+                lo = __ldcg(reinterpret_cast<const float2*>(src + (int64_t)(m0 + g) * V));
+                hi = __ldcg(reinterpret_cast<const float2*>(src + (int64_t)(m0 + g + 8) * V));
             }
             dS[hh][nt][0] = lo.x; dS[hh][nt][1] = lo.y; dS[hh][nt][2] = hi.x; dS[hh][nt][3] = hi.y;
         }
@@ -310,12 +341,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
         load_tile<LD64, 64>(smem + oS, sb + oS, sg + (cs_blk0 + (int64_t)cc * cs_blk_stride) * V * 64, 64, 128, min(128, V), tid);
         cp_async_commit();
     };
-    if (NC > 0) issue_chunk_loads(NC - 1, 0);
+    if (c_hi >= c_lo) issue_chunk_loads(c_hi, 0);
 
     BT_DECL
-    for (int c = NC - 1; c >= 0; --c) {
+    for (int c = c_hi; c >= c_lo; --c) {
         const int t0 = c << 6, valid = min(64, T - t0);
-        const int par = (NC - 1 - c) & 1;
+        const int par = (c_hi - c) & 1;
         const uint32_t oK = oKQ + (uint32_t)par * 2 * SZ64, oQ = oK + SZ64;
         const __nv_bfloat16* sc_ptr = sg + (cs_blk0 + (int64_t)c * cs_blk_stride) * V * 64;       // chunk-start state [V][64]
         if (warp == 0) {        // gates of the chunk: lane l holds tokens 2l, 2l + 1; pad tokens g = 0, beta = 0 (exact no-ops)
@@ -515,7 +546,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
                 load_tile<LD128, 128>(smem + odO, sb + odO, dog + (int64_t)t0 * p.do_stride[1] + (hh + 1) * 128, p.do_stride[1], 64, valid, tid);
                 load_tile<LD64, 64>(smem + oS, sb + oS, sc_ptr + (hh + 1) * 128 * 64, 64, 128, 128, tid);
                 cp_async_commit();
-            } else if (c > 0) {
+            } else if (c > c_lo) {
                 issue_chunk_loads(c - 1, par ^ 1);
             }
             {   // dV half -> global (16-byte stores, valid rows only)
@@ -707,18 +738,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
         SYNC(15);
     }
 
-    if (p.d_initial_state != nullptr) {
+    float* ds_dst = seg == nseg - 1 || nseg <= 1 ? p.d_initial_state : xstate;     // the caller's gradient | hand-off to the earlier segment
+    if (ds_dst != nullptr) {
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int col = hh * 128 + n128 + nt * 8 + 2 * t;
                 if (col < V) {
-                    float* dst = p.d_initial_state + (int64_t)chain * 64 * V + col;
+                    float* dst = ds_dst + (int64_t)chain * 64 * V + col;
                     *reinterpret_cast<float2*>(dst + (int64_t)(m0 + g) * V) = make_float2(dS[hh][nt][0], dS[hh][nt][1]);
                     *reinterpret_cast<float2*>(dst + (int64_t)(m0 + g + 8) * V) = make_float2(dS[hh][nt][2], dS[hh][nt][3]);
                 }
             }
+    }
+    if (nseg > 1 && seg < nseg - 1) {    // publish: the state-cotangent writes of all threads, then the flag
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) sm100::st_release_gpu(xsync + 1 + chain, seg + 1);
     }
 }
 
@@ -753,10 +790,41 @@ int launch_bwd(const GdkvmGdrBwdParams& p, cudaStream_t stream) {
         }
     }
     const int chains = (p.cu_seqlens != nullptr ? p.n_seqs : p.B) * p.H;
-    if (p.V > 128) gdr_bwd_kernel<2><<<chains, kBwdThreads, kBwdSmem + 1024, stream>>>(p);
-    else gdr_bwd_kernel<1><<<chains, kBwdThreads, kBwdSmem + 1024, stream>>>(p);
+    // time segments (batched call only): explicit count in flags bits 8-11, else the schedule simulation's choice
+    int nseg = 1, seg_chunks = 0, sms = 148;
+    bool mempools = false;
+    float* xstate = nullptr;
+    int* xsync = nullptr;
+    void* ws = nullptr;
+    if (p.cu_seqlens == nullptr) {
+        const int nc = (p.T + 63) / 64;
+        (void)library_scratch_alloc(nullptr, 0, stream, &sms, &mempools);
+        nseg = (int)((p.flags >> 8) & 0xfu);
+        if (nseg == 0) nseg = plan_time_segments(chains, nc, sms);
+        nseg = std::max(1, std::min(nseg, nc));
+        seg_chunks = (nc + nseg - 1) / nseg;
+        nseg = (nc + seg_chunks - 1) / seg_chunks;                 // no empty segment
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
+        if (cap != cudaStreamCaptureStatusNone && !mempools) nseg = 1;
+        if (nseg > 1) {
+            const size_t state_bytes = (size_t)chains * 64 * p.V * sizeof(float), sync_bytes = ((size_t)chains + 1) * sizeof(int);
+            if (library_scratch_alloc(&ws, state_bytes + sync_bytes, stream, nullptr, nullptr) != 0) {
+                ws = nullptr; nseg = 1;                            // same kernel, uncut chains
+            } else {
+                xstate = reinterpret_cast<float*>(ws);
+                xsync = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + state_bytes);
+                const cudaError_t me = cudaMemsetAsync(xsync, 0, sync_bytes, stream);
+                if (me != cudaSuccess) { cudaFreeAsync(ws, stream); return (int)me; }
+            }
+        }
+    }
+    if (p.V > 128) gdr_bwd_kernel<2><<<chains * nseg, kBwdThreads, kBwdSmem + 1024, stream>>>(p, nseg, seg_chunks, xstate, xsync);
+    else gdr_bwd_kernel<1><<<chains * nseg, kBwdThreads, kBwdSmem + 1024, stream>>>(p, nseg, seg_chunks, xstate, xsync);
     count_launch();
-    return (int)cudaGetLastError();
+    const cudaError_t le = cudaGetLastError();
+    if (ws != nullptr) cudaFreeAsync(ws, stream);
+    return (int)le;
 }
 
 }  // namespace gdkvm

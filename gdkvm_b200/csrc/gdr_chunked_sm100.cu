@@ -1195,6 +1195,19 @@ __global__ void __launch_bounds__(256) gdr_units_kernel(const IdxT* __restrict__
 
 }  // namespace
 
+int plan_time_segments(int chains, int chunks, int sms) { return pick_segments(chains, chunks, sms > 0 ? sms : 148); }
+
+int library_scratch_alloc(void** ws, size_t bytes, cudaStream_t stream, int* sms, bool* mempools) {
+    const DeviceCtx* dc = device_ctx();
+    if (dc == nullptr) return (int)cudaErrorInvalidDevice;
+    if (sms != nullptr) *sms = dc->sms;
+    if (mempools != nullptr) *mempools = dc->mempools;
+    if (ws == nullptr) return 0;
+    const cudaError_t e = scratch_alloc(ws, bytes, dc, stream);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    return (int)e;
+}
+
 int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream, void* chunk_states) {
     const DeviceCtx* dc = device_ctx();
     if (dc == nullptr) return (int)cudaErrorInvalidDevice;

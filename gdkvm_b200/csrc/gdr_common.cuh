@@ -25,6 +25,11 @@ const char* chunked_unsupported_reason(const GdkvmGdrParams& p);
 // Time segments per chain the chunked kernel would use on a device with `sms` SMs (host-side schedule simulation).
 int chunked_segments(const GdkvmGdrParams& p, int sms);
 
+// Shared host helpers (gdr_chunked_sm100.cu): the schedule simulation behind the time segments, and a stream-ordered scratch
+// allocation from the library's private per-device pool (*sms receives the device's SM count).  Return cudaError_t as int.
+int plan_time_segments(int chains, int chunks, int sms);
+int library_scratch_alloc(void** ws, size_t bytes, cudaStream_t stream, int* sms, bool* mempools);
+
 // Backward pass (gdr_bwd_sm100.cu)
 int launch_bwd(const GdkvmGdrBwdParams& p, cudaStream_t stream);
 const char* bwd_unsupported_reason(const GdkvmGdrBwdParams& p);

@@ -177,7 +177,7 @@ torch.library.define(
 torch.library.define(
     "gdkvm::gdr_lkva_bwd",
     "(Tensor q, Tensor k, Tensor v, Tensor g, Tensor beta, Tensor chunk_states, Tensor d_o, Tensor? d_final_state, float scale, "
-    "bool need_d_initial_state, Tensor? cu_seqlens=None) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)",
+    "bool need_d_initial_state, Tensor? cu_seqlens=None, int flags=0) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)",
 )
 torch.library.define(
     "gdkvm::gdr_lkva_varlen_train",
@@ -235,7 +235,7 @@ def _gdr_lkva_train_fake(q, k, v, g, beta, scale=None, initial_state=None, flags
 
 
 @torch.library.impl("gdkvm::gdr_lkva_bwd", "CUDA")
-def _gdr_lkva_bwd_cuda(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale, need_d_initial_state, cu_seqlens=None):
+def _gdr_lkva_bwd_cuda(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale, need_d_initial_state, cu_seqlens=None, flags=0):
     _check(q, k, v, g, beta, None)
     _same_device(q, chunk_states=chunk_states, d_o=d_o, d_final_state=d_final_state, cu_seqlens=cu_seqlens)
     B, T, H, K = k.shape
@@ -261,6 +261,7 @@ def _gdr_lkva_bwd_cuda(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale
     lib = _cabi.load()
     p = _cabi.GdkvmGdrBwdParams()
     p.struct_size = ctypes.sizeof(_cabi.GdkvmGdrBwdParams)
+    p.flags = int(flags) & 0xF00
     p.q, p.k, p.v, p.g, p.beta = q.data_ptr(), k.data_ptr(), v.data_ptr(), g.data_ptr(), beta.data_ptr()
     p.d_o = d_o.data_ptr()
     p.d_final_state = d_final_state.data_ptr() if d_final_state is not None else None
@@ -284,7 +285,7 @@ def _gdr_lkva_bwd_cuda(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale
 
 
 @torch.library.register_fake("gdkvm::gdr_lkva_bwd")
-def _gdr_lkva_bwd_fake(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale, need_d_initial_state, cu_seqlens=None):
+def _gdr_lkva_bwd_fake(q, k, v, g, beta, chunk_states, d_o, d_final_state, scale, need_d_initial_state, cu_seqlens=None, flags=0):
     B, T, H, K = k.shape
     V = v.shape[-1]
     NS = B if cu_seqlens is None else cu_seqlens.shape[0] - 1

@@ -195,7 +195,8 @@ int64_t gdkvm_gdr_chunk_states_bytes_varlen(int32_t T, int32_t n_seqs, int32_t H
  */
 typedef struct GdkvmGdrBwdParams {
     uint32_t struct_size;        /* = sizeof(GdkvmGdrBwdParams)                                */
-    uint32_t flags;              /* reserved, 0                                                */
+    uint32_t flags;              /* GDKVM_FLAG_SEGMENTS(n): cut every chain into n time segments (separate work units, the state
+                                    cotangent handed over in fp32: bit-identical results); 0 = the library chooses           */
     const void* q;
     const void* k;
     const void* v;
