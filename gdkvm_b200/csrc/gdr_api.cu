@@ -173,7 +173,7 @@ int gdkvm_gdr_fwd_train(const GdkvmGdrParams* params, void* chunk_states, void* 
     int rc = gdkvm::validate(params);
     if (rc != GDKVM_OK) return rc;
     if (params->flags & GDKVM_FLAG_FORCE_RECURRENT) return GDKVM_ERR_UNSUPPORTED;
-    if (!gdkvm::chunked_supports(*params) || (params->V != 128 && params->V != 256)) return params->T == 0 ? GDKVM_ERR_SHAPE : GDKVM_ERR_UNSUPPORTED;
+    if (!gdkvm::chunked_supports(*params)) return params->T == 0 ? GDKVM_ERR_SHAPE : GDKVM_ERR_UNSUPPORTED;
     if (chunk_states == nullptr) return GDKVM_ERR_NULL;
     if (reinterpret_cast<uintptr_t>(chunk_states) & 15u) return GDKVM_ERR_ALIGN;
     bool sm100 = false;
@@ -200,7 +200,7 @@ int gdkvm_gdr_fwd_train_varlen(const GdkvmGdrParams* params, const void* cu_seql
     if ((int64_t)n_seqs * params->H > 0x3fffffff) return GDKVM_ERR_SHAPE;
     if (params->flags & GDKVM_FLAG_FORCE_RECURRENT) return GDKVM_ERR_UNSUPPORTED;
     if (params->T == 0) return GDKVM_ERR_SHAPE;
-    if (!gdkvm::chunked_supports(*params) || (params->V != 128 && params->V != 256)) return GDKVM_ERR_UNSUPPORTED;
+    if (!gdkvm::chunked_supports(*params)) return GDKVM_ERR_UNSUPPORTED;
     bool sm100 = false;
     int ce = gdkvm::device_is_sm100(&sm100);
     if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }

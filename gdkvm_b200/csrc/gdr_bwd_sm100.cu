@@ -336,11 +336,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
         const uint32_t ok = oKQ + (uint32_t)par * 2 * SZ64;
         load_tile<LD64, 64>(smem + ok, sb + ok, kg + (int64_t)tt * p.k_stride[1], p.k_stride[1], 64, vld, tid);
         load_tile<LD64, 64>(smem + ok + SZ64, sb + ok + SZ64, qg + (int64_t)tt * p.q_stride[1], p.q_stride[1], 64, vld, tid);
-        load_tile<LD128, 128>(smem + oV, sb + oV, vg + (int64_t)tt * p.v_stride[1], p.v_stride[1], 64, vld, tid);
-        load_tile<LD128, 128>(smem + odO, sb + odO, dog + (int64_t)tt * p.do_stride[1], p.do_stride[1], 64, vld, tid);
+        if (V >= 128) {
+            load_tile<LD128, 128>(smem + oV, sb + oV, vg + (int64_t)tt * p.v_stride[1], p.v_stride[1], 64, vld, tid);
+            load_tile<LD128, 128>(smem + odO, sb + odO, dog + (int64_t)tt * p.do_stride[1], p.do_stride[1], 64, vld, tid);
+        } else {            // d_v = 64: the right half of the 128-column tiles stays zero (cleared once below)
+            load_tile<LD128, 64>(smem + oV, sb + oV, vg + (int64_t)tt * p.v_stride[1], p.v_stride[1], 64, vld, tid);
+            load_tile<LD128, 64>(smem + odO, sb + odO, dog + (int64_t)tt * p.do_stride[1], p.do_stride[1], 64, vld, tid);
+        }
         load_tile<LD64, 64>(smem + oS, sb + oS, sg + (cs_blk0 + (int64_t)cc * cs_blk_stride) * V * 64, 64, 128, min(128, V), tid);
         cp_async_commit();
     };
+    if (V < 128) {          // d_v = 64: value columns 64-127 of the V and dO tiles are never loaded
+        for (int i = tid; i < 64 * 8; i += kBwdThreads) {
+            const int r = i >> 3, cc = 64 + (i & 7) * 8;
+            *reinterpret_cast<uint4*>(smem + oV + (r * LD128 + cc) * 2) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(smem + odO + (r * LD128 + cc) * 2) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+    }
     if (c_hi >= c_lo) issue_chunk_loads(c_hi, 0);
 
     BT_DECL
@@ -764,7 +777,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
 const char* bwd_unsupported_reason(const GdkvmGdrBwdParams& p) {
     if (p.io_dtype != GDKVM_BF16) return "backward: q/k/v/do must be bf16 (the training forward keeps bf16 chunk states)";
     if (p.K != 64) return "backward: d_k must be 64";
-    if (p.V != 128 && p.V != 256) return "backward: d_v must be 128 or 256";
+    if (p.V != 64 && p.V != 128 && p.V != 256) return "backward: d_v must be 64, 128 or 256";
     const void* ptrs[8] = {p.q, p.k, p.v, p.d_o, p.dq, p.dk, p.dv, p.chunk_states};
     for (const void* x : ptrs) if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0) return "backward: tensor bases must be 16-byte aligned";
     for (int i = 0; i < 3; ++i) {

@@ -190,8 +190,8 @@ def train_unsupported_reason(q, k, v) -> str:
     """Why the training path (forward that keeps chunk states + backward kernel) cannot take these tensors ("" if it can)."""
     if q.dtype != torch.bfloat16:
         return "the backward pass takes bf16 q/k/v (fp32 I/O has no training path)"
-    if k.shape[-1] != 64 or v.shape[-1] not in (128, 256):
-        return "the backward pass is built for d_k = 64 and d_v in {128, 256}"
+    if k.shape[-1] != 64 or v.shape[-1] not in (64, 128, 256):
+        return "the backward pass is built for d_k = 64 and d_v in {64, 128, 256}"
     return ""
 
 
@@ -381,7 +381,7 @@ def _no_backward(name):
         raise NotImplementedError(
             f"torch.ops.gdkvm.{name} has no backward formula: differentiate through gdkvm_b200.gdr_lkva / GDRMemory / "
             "gdr_lkva_varlen / chunk_gated_delta_rule (they route a call that needs gradients to the training forward: bf16, "
-            "d_k = 64, d_v in {128, 256})")
+            "d_k = 64, d_v in {64, 128, 256})")
     return backward
 
 
@@ -606,7 +606,7 @@ def gdr_lkva(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, g: torch.Tensor,
     q,k [B,T,H,K]; v [B,T,H,V]; g (log-space gate) and beta [B,T,H]; initial_state fp32 [B,H,K,V].
     Returns ``(o [B,T,H,V] in q.dtype, final_state fp32 [B,H,K,V] or None)``.
     ``frame_tokens=C`` declares T = F*C with every frame one chunk (north_star).
-    Differentiable (bf16, d_k = 64, d_v in {128, 256}): when gradients are enabled and an input requires them, the call
+    Differentiable (bf16, d_k = 64, d_v in {64, 128, 256}): when gradients are enabled and an input requires them, the call
     runs the training forward and autograd runs the hand-written backward kernel (csrc/gdr_bwd_sm100.cu).
     """
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (q, k, v, g, beta, initial_state)):

@@ -170,7 +170,7 @@ int gdkvm_l2norm_fwd(const void* x, void* y, int64_t rows, int32_t D, int64_t x_
  *   replaces: the autograd formula of the reference memory module (the upstream model is trained: reference
  *   website/src/pages/[lang]/reprod/index.astro:238-252; shape of the work: fla/ops/gated_delta_rule/chunk.py:117).
  *
- * gdkvm_gdr_fwd_train = gdkvm_gdr_fwd on the tcgen05 chunk kernel (bf16 I/O, K = 64, V in {128, 256}; anything else returns
+ * gdkvm_gdr_fwd_train = gdkvm_gdr_fwd on the tcgen05 chunk kernel (bf16 I/O, K = 64, V in {64, 128, 256}; anything else returns
  * GDKVM_ERR_UNSUPPORTED -- there is no slow training path) which ALSO writes the bf16 state at the start of every 64-token
  * chunk into `chunk_states`, a caller-owned device buffer of gdkvm_gdr_chunk_states_bytes(B, T, H, K, V) bytes laid out
  * [B*H][ceil(T/64)][V][K].  The token stream is tiled flat in 64-token chunks (frame_tokens is ignored; results equal

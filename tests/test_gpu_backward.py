@@ -46,6 +46,7 @@ def _grads_on_device(op, q, k, v, g, beta, S0, do, dsT):
     (2, 5 * 49, 3, 256, 49, True, True, False),         # EchoNet-shaped frames, correlated keys, no final-state cotangent
     (1, 37, 2, 128, 0, False, False, True),             # less than a chunk, zero initial state
     (1, 8 * 64, 2, 256, 0, False, True, True),          # eight chunks: the state cotangent carried a long way
+    (2, 3 * 64 + 5, 3, 64, 0, True, True, True),        # d_v = 64: half-empty value tiles
 ])
 def test_backward_vs_float64_autograd(op, case):
     B, T, H, V, C, corr, w_s0, w_dsT = case
@@ -153,8 +154,8 @@ def test_what_cannot_be_differentiated_says_so(op):
     o, _ = torch.ops.gdkvm.gdr_lkva_varlen(qb, kb, vb, g.cuda(), beta.cuda(), cu)                    # the raw packed inference op
     with pytest.raises(NotImplementedError, match="no backward formula"):
         o.float().sum().backward()
-    with pytest.raises(NotImplementedError):                                                         # d_v = 64
-        op.gdr_lkva(qb, kb, vb[..., :64].contiguous().requires_grad_(True), g.cuda(), beta.cuda())
+    with pytest.raises(NotImplementedError):                                                         # d_v = 32
+        op.gdr_lkva(qb, kb, vb[..., :32].contiguous().requires_grad_(True), g.cuda(), beta.cuda())
 
 
 def test_l2norm_is_differentiable(op):
