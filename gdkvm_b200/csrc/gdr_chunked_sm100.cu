@@ -324,7 +324,9 @@ struct FastDiv {
 // [6] chunk-state slot of the first chunk (training forward)
 constexpr int kUnitInts = 8;
 
-template <bool kVar>
+// kSave: the training forward (also stores the bf16 chunk-start states) -- a separate instantiation, so that the inference
+// kernel's S pass, which is on the recurrence, carries neither the branch nor its register pressure (it cost 2.4 % as a run-time test)
+template <bool kVar, bool kSave>
 __global__ void __launch_bounds__(kThreads, 1)
 gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__ CUtensorMap mk,
                  const __grid_constant__ CUtensorMap mv, const __grid_constant__ CUtensorMap mo,
@@ -732,7 +734,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                             pk[16 + j] = pack_bf16(__uint_as_float(rb[2 * j]), __uint_as_float(rb[2 * j + 1]));
                         }
                         tmem_st32(lane_addr + kColSb + hh * 32, pk);
-                        if (sdump != nullptr) {
+                        if constexpr (kSave) {
                             // training forward: the bf16 chunk-start state (exactly the operand copy Sb) is kept for the backward
                             // pass -- batched: [chain][chunk][value column][key dim]; packed clips: [slot][head][value column][key dim]
                             // -- 128 contiguous bytes per thread
@@ -1027,8 +1029,10 @@ DeviceCtx* device_ctx() {
         c->init = true;
     }
     if (c->attr_err != cudaSuccess) {      // retried until it has succeeded on THIS device
-        cudaError_t e = cudaFuncSetAttribute(gdr_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(gdr_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(gdr_chunk_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gdr_chunk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gdr_chunk_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(gdr_chunk_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
         if (e != cudaSuccess) (void)cudaGetLastError();
         c->attr_err = e;
     }
@@ -1250,9 +1254,13 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream, void* chunk_sta
             if (me2 != cudaSuccess) { cudaFreeAsync(ws, stream); return (int)me2; }
         }
     }
-    gdr_chunk_kernel<false><<<chains * nseg, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, C, F, FastDiv::make((unsigned)cpf),
-                                                                             nseg, seg_chunks, xstate, xsync, nullptr,
-                                                                             reinterpret_cast<__nv_bfloat16*>(chunk_states));
+    if (chunk_states != nullptr)
+        gdr_chunk_kernel<false, true><<<chains * nseg, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, C, F, FastDiv::make((unsigned)cpf),
+                                                                                       nseg, seg_chunks, xstate, xsync, nullptr,
+                                                                                       reinterpret_cast<__nv_bfloat16*>(chunk_states));
+    else
+        gdr_chunk_kernel<false, false><<<chains * nseg, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, C, F, FastDiv::make((unsigned)cpf),
+                                                                                        nseg, seg_chunks, xstate, xsync, nullptr, nullptr);
     count_launch();
     const cudaError_t le = cudaGetLastError();
     if (ws != nullptr) cudaFreeAsync(ws, stream);
@@ -1301,8 +1309,12 @@ int launch_chunked_varlen(const GdkvmGdrParams& p, const void* cu, int cu_bytes,
         gdr_units_kernel<int><<<1, 256, 0, stream>>>(reinterpret_cast<const int*>(cu), nseq, seg_chunks, max_entries, utab, H, 64 * V,
                                                      p.initial_state, p.final_state);
     count_launch();
-    gdr_chunk_kernel<true><<<max_entries * H, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, p.T, 1, FastDiv::make(1u), 0, 0, xstate,
-                                                                              xsync, utab, reinterpret_cast<__nv_bfloat16*>(chunk_states));
+    if (chunk_states != nullptr)
+        gdr_chunk_kernel<true, true><<<max_entries * H, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, p.T, 1, FastDiv::make(1u), 0, 0, xstate,
+                                                                                        xsync, utab, reinterpret_cast<__nv_bfloat16*>(chunk_states));
+    else
+        gdr_chunk_kernel<true, false><<<max_entries * H, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, p, p.T, 1, FastDiv::make(1u), 0, 0,
+                                                                                         xstate, xsync, utab, nullptr);
     count_launch();
     const cudaError_t le = cudaGetLastError();
     cudaFreeAsync(ws, stream);
