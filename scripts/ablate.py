@@ -4,7 +4,7 @@ import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 NAMES = ["gating", "solve L0-1", "solve L2", "T' conversion", "W^T", "S pass", "Vnb pass", "readout"]
-MASKS = [0] + [1 << i for i in range(8)] + [0x0f, 0x1f, 0xf0, 0xe0, 0xff]
+MASKS = [0] + [int(x, 16) for x in os.environ.get("MASKS", "01 02 04 08 10 20 40 80 0f 1f f0 e0 ff").split()]
 lib = lambda m: os.path.join(ROOT, "gdkvm_b200", f"libgdkvm_gdr_abl{m:02x}.so")
 if len(sys.argv) > 1 and sys.argv[1] == "build":
     from gdkvm_b200 import _build
@@ -16,7 +16,7 @@ for m in MASKS:
     env = dict(os.environ)
     if m:
         env["GDKVM_LIB"] = lib(m)
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "10", "--warmup", "3", "--no-e2e", "--no-cpu"],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "20", "--warmup", "5", "--no-e2e", "--no-cpu", "--no-extras", "--sustained-seconds", "0"],
                          capture_output=True, text=True, env=env)
     try:
         ms = json.loads(out.stdout.strip().splitlines()[-1])["ms_per_step"]

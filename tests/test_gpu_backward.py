@@ -91,6 +91,26 @@ def test_backward_of_packed_variable_length_clips(op, cu_dtype):
             assert max_rel_err(xx, r.float()) <= 2e-2, (n, name)
 
 
+def test_backward_with_strong_decay_and_bf16_gates(op):
+    """Chunks whose total decay is far below e^-60 (the forward kernel's slow path; exp(Gamma) underflows to zero inside the
+    chunk) mixed with ordinary ones, and gates / beta given in bf16 (their gradients come back in bf16)."""
+    q, k, v, g, beta, S0, do, dsT = _case(2, 5 * 64, 2, 256, 601)
+    g = g.clone()
+    g[:, 64:192] *= 300.0
+    ref = gdr_backward_ref(q, k, v, g, beta, do, dsT, None, S0)
+    got, o, sT = _grads_on_device(op, q, k, v, g, beta, S0, do, dsT)
+    for name, a, b in zip(NAMES, got, ref):
+        assert bool(torch.isfinite(a).all()), name
+        assert max_rel_err(a, b.float()) <= 2e-2, (name, max_rel_err(a, b.float()))
+    q, k, v, g, beta, S0, do, dsT = _case(1, 130, 2, 128, 602)
+    gb, bb = g.bfloat16(), beta.bfloat16()
+    ref = gdr_backward_ref(q, k, v, gb, bb, do, dsT, None, S0)
+    got, _, _ = _grads_on_device(op, q, k, v, gb, bb, S0, do, dsT)
+    for name, a, b in zip(NAMES, got, ref):
+        tol = 2e-2 if name not in ("dg", "dbeta") else 3e-2          # + one bf16 rounding of the returned gate gradients
+        assert max_rel_err(a, b.float()) <= tol, (name, max_rel_err(a, b.float()))
+
+
 def test_training_forward_is_the_inference_forward(op):
     """gdr_lkva_train = the tcgen05 kernel on flat 64-token chunks, bit for bit, plus the bf16 chunk-start states."""
     q, k, v, g, beta, S0, _, _ = _case(3, 5 * 64 + 7, 2, 256, 301)
