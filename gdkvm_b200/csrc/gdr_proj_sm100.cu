@@ -233,6 +233,7 @@ qkvgb_proj_kernel(const __grid_constant__ CUtensorMap mx, const __grid_constant_
 
 const char* proj_unsupported_reason(const GdkvmProjParams& p) {
     if (p.K != 64) return "projection: d_k must be 64";
+    if (p.R >= (int64_t)1 << 31) return "projection: at most 2^31 - 1 rows per call (TMA coordinates are 32-bit)";
     if (p.H < 2 || p.H > 32 || (p.H & 1)) return "projection: the number of heads must be even, 2..32";
     if (p.V <= 0 || p.V % 64 != 0) return "projection: d_v must be a multiple of 64";
     if (p.D <= 0 || p.D % 64 != 0 || p.D > 512) return "projection: the feature dimension must be a multiple of 64, at most 512";
