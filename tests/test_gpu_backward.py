@@ -111,6 +111,29 @@ def test_backward_with_strong_decay_and_bf16_gates(op):
         assert max_rel_err(a, b.float()) <= tol, (name, max_rel_err(a, b.float()))
 
 
+def test_backward_over_a_long_clip_does_not_drift(op):
+    """64 frames x 49 tokens = 49 chunks (the state cotangent is carried through all of them, with time segments forced so
+    that it also crosses two hand-offs): every gradient within tolerance, and the error of dq / dk / dv over the FIRST quarter
+    of the clip -- the far end of the reverse scan -- no worse than twice that of the last quarter."""
+    T = 64 * 49
+    q, k, v, g, beta, S0, do, dsT = _case(1, T, 1, 256, 701, 49, True)
+    ref = gdr_backward_ref(q, k, v, g, beta, do, dsT, None, S0)
+    qd, kd, vd, gd, bd, sd = (x.cuda() for x in (q, k, v, g, beta, S0))
+    _, _, cs = torch.ops.gdkvm.gdr_lkva_train(qd, kd, vd, gd, bd, None, sd, 0)
+    got = torch.ops.gdkvm.gdr_lkva_bwd(qd, kd, vd, gd, bd, cs, do.cuda(), dsT.cuda(), 0.125, True, None, 3 << 8)
+    torch.cuda.synchronize()
+    for name, a, b in zip(NAMES, got, ref):
+        e = max_rel_err(a, b.float())
+        print(f"long clip: {name} max-rel {e:.2e}")
+        assert e <= 2e-2, (name, e)
+    for name, a, b in zip(NAMES[:3], got[:3], ref[:3]):
+        a, b = a.float().cpu(), b.float()
+        den = b.abs().max()
+        first = float((a[:, :T // 4] - b[:, :T // 4]).abs().max() / den)
+        last = float((a[:, -T // 4:] - b[:, -T // 4:]).abs().max() / den)
+        assert first <= max(2.0 * last, 5e-3), (name, first, last)
+
+
 def test_training_forward_is_the_inference_forward(op):
     """gdr_lkva_train = the tcgen05 kernel on flat 64-token chunks, bit for bit, plus the bf16 chunk-start states."""
     q, k, v, g, beta, S0, _, _ = _case(3, 5 * 64 + 7, 2, 256, 301)
