@@ -84,3 +84,26 @@ def test_projection_is_differentiable_and_rejects_bad_shapes(op):
         op.qkvgb_project(x.cuda(), w.cuda()[:-1], None, 2, 64, 128)
     with pytest.raises(RuntimeError, match="does not support"):
         op.qkvgb_project(x.cuda(), torch.zeros(3 * (128 + 128) + 6, 128, dtype=torch.bfloat16, device="cuda"), None, 3, 64, 128)   # odd H
+
+
+def test_projection_full_size_properties(op):
+    """configs[1] geometry (401 408 tokens, D = 256, 8 heads, d_v = 256 -> 3 088 columns; 3 136 row blocks over all SMs): every q / k row
+    has unit norm, gates are <= 0 and beta in (0, 1), and three row blocks (first, one in the middle of a CTA's walk, the ragged
+    last one) agree with the fp32 reference."""
+    R, D, H, V = 64 * 6272 - 37, 256, 8, 256                     # a ragged last row block
+    gen = torch.Generator(device="cuda").manual_seed(900)
+    x = torch.randn(R, D, generator=gen, device="cuda").bfloat16()
+    w = (torch.randn(H * (128 + V) + 2 * H, D, generator=gen, device="cuda") / D ** 0.5).bfloat16()
+    b = 0.1 * torch.randn(w.shape[0], generator=gen, device="cuda")
+    q, k, v, g, beta = op.qkvgb_project(x, w, b, H, 64, V)
+    torch.cuda.synchronize()
+    for t in (q, k):
+        n = t.float().norm(dim=-1)
+        assert float((n - 1).abs().max()) < 1e-2
+    assert float(g.max()) <= 0 and float(beta.min()) > 0 and float(beta.max()) < 1 and bool(torch.isfinite(v.float()).all())
+    for r0 in (0, 128 * 1777, (R // 128) * 128):
+        sl = slice(r0, min(R, r0 + 128))
+        ref = _fp32_reference(x[sl].cpu(), w.cpu(), b.cpu(), H, 64, V)
+        for name, a, r in zip(("q", "k", "v", "g", "beta"), (q, k, v, g, beta), ref):
+            tol = 2.0 ** -8 * max(1.0, float(r.abs().max())) if name in ("q", "k", "v") else 2e-4
+            assert float((a[sl].float().cpu() - r).abs().max()) <= tol, (name, r0)
