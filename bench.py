@@ -424,8 +424,23 @@ def run_extras(args, dev, sampler, main_inputs, main_ms):
                 qq, kk, vv, gg, bb = gdkvm_b200.qkvgb_project(tok, wq, bq, 8, 64, 256)
                 gdkvm_b200.gdr_lkva(qq, kk, vv, gg, bb, None, None, True, 49)
             ms_m, _, _ = time_for(mem, args.extra_seconds / 2)
+        # one training step of the same model (forward, BCE loss, backward through the memory op's backward kernel), 2 clips
+        train_ms = None
+        try:
+            model.train()
+            clip2 = clip[:2]
+            tgt = (torch.rand(2, Fr, 1, 112, 112, device=dev) > 0.5).float()
+
+            def train_step():
+                model.zero_grad(set_to_none=True)
+                lg, _ = model(clip2)
+                torch.nn.functional.binary_cross_entropy_with_logits(lg.float(), tgt).backward()
+            train_ms, _, _ = time_for(train_step, args.extra_seconds / 2, warmup=2, min_steps=2)
+        except Exception as ex:  # noqa: BLE001
+            train_ms = repr(ex)[:200]
         return {"ms_per_step": ms, "steps": steps, "value": Bc * Fr / (ms * 1e-3), "unit": "frames/s (end to end)",
                 "clips": Bc, "frames": Fr, "memory_path_ms": ms_m, "memory_path_share": ms_m / ms,
+                "train_step_2_clips_ms": train_ms,
                 "clocks": sampler.window(*win) if sampler is not None else None,
                 "note": "BASELINE configs[4] skeleton: random-init stand-in encoder / KPFF / decoder in plain PyTorch (cuDNN), bf16, 8 clips x "
                         "128 frames x 112x112; memory path = fused projection kernel + tcgen05 memory op (this package)"}
