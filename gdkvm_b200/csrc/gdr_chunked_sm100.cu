@@ -50,6 +50,9 @@
 // of a sequence carry the NEXT sequence's tokens: g = beta = 0 makes them exact no-ops of the recurrence, and the
 // last chunk's readout is stored row by row instead of by TMA so that nothing is written past the sequence.
 //
+// Training forward (kSave): a second instantiation whose S pass also stores the bf16 operand copy Sb of every chunk-start state
+// (the only thing the backward kernel, gdr_bwd_sm100.cu, needs from the forward).
+//
 // Layout facts used here were verified on hardware by tests/probes/umma_probe.cu.
 // Math: oracle/gdr_ref.py::gdr_chunk_ref.
 #include <algorithm>

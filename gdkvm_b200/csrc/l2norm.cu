@@ -3,7 +3,8 @@
 // SURVEY.md section 8f rank 3 (the step immediately before the op; fla's `use_qk_l2norm_in_kernel`,
 // fla/ops/gated_delta_rule/chunk.py:374).  This is the UNFUSED first step: one streaming pass, 16-byte vector loads and
 // stores, D/8 (bf16) or D/4 (fp32) lanes per row with a shuffle reduction; HBM-bound (reads and writes every byte once).
-// Folding it into the chunk kernel (the diagonal of K K^T already holds |k_j|^2) is the follow-up.
+// Folding it into the chunk kernel was measured and rejected; when q and k come out of a projection, the
+// fused projection kernel (gdr_proj_sm100.cu) normalises them in its epilogue and this pass is not needed at all.
 #include "gdr_common.cuh"
 
 namespace gdkvm {
