@@ -245,9 +245,11 @@ int gdkvm_gdr_bwd(const GdkvmGdrBwdParams* params, void* cuda_stream);
  *   g <- logsigmoid(y_g), beta <- sigmoid(y_beta) -> fp32 [R, H].   K = 64, H even (2..32), V % 64 == 0, D % 64 == 0.
  * A tcgen05 GEMM (TMA-staged operands, TMEM accumulators) whose epilogue writes the op-ready tensors: y never touches HBM.
  */
+#define GDKVM_PROJ_FLAG_TILE_ROWS_128 1u   /* force 128-token row blocks (128 x 256 output tiles)                       */
+#define GDKVM_PROJ_FLAG_TILE_ROWS_256 2u   /* force 256-token row blocks (256 x 128 output tiles; needs D <= 256)       */
 typedef struct GdkvmProjParams {
     uint32_t struct_size;        /* = sizeof(GdkvmProjParams)                                  */
-    uint32_t flags;              /* reserved, 0                                                */
+    uint32_t flags;              /* 0 = the library picks the tile shape; GDKVM_PROJ_FLAG_*    */
     const void* x;
     const void* w;
     const float* bias;           /* [N] fp32, may be NULL                                      */

@@ -38,9 +38,17 @@ def _make(lead, D, H, V, seed, bias):
     ((3, 128), 64, 2, 64, False),         # one k-block, smallest head count
     ((2, 77), 512, 4, 128, True),         # eight k-blocks through the three-stage ring
     ((1, 5), 128, 6, 192, False),         # fewer rows than one tile; d_v = 192
+    ((700,), 256, 8, 256, True),          # three 256-row blocks, the last ragged
 ])
-def test_projection_vs_fp32_linear(op, case):
+@pytest.mark.parametrize("tile_rows", ["128", "256"])     # both tile shapes of the kernel (the library picks by problem size)
+def test_projection_vs_fp32_linear(op, case, tile_rows, monkeypatch):
     lead, D, H, V, bias = case
+    monkeypatch.setenv("GDKVM_PROJ_TILE_ROWS", tile_rows)
+    if tile_rows == "256" and D > 256:
+        with pytest.raises(RuntimeError, match="does not support"):
+            x, w, b = _make(lead, D, H, V, 500 + D, bias)
+            op.qkvgb_project(x.cuda(), w.cuda(), None, H, 64, V)
+        return
     x, w, b = _make(lead, D, H, V, 500 + D, bias)
     ref = _fp32_reference(x, w, b, H, 64, V)
     got = op.qkvgb_project(x.cuda(), w.cuda(), b.cuda() if b is not None else None, H, 64, V)
