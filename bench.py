@@ -372,22 +372,23 @@ def run_extras(args, dev, sampler, main_inputs, main_ms):
         gen = torch.Generator(device=dev).manual_seed(55)
         x = torch.randn(B, T, D, generator=gen, device=dev, dtype=torch.float32).bfloat16()
         w = (torch.randn(N, D, generator=gen, device=dev, dtype=torch.float32) / D ** 0.5).bfloat16()
+        bias = 0.1 * torch.randn(N, generator=gen, device=dev, dtype=torch.float32)      # the model's projection has one
         o2 = torch.empty(B, T, H, V, dtype=torch.bfloat16, device=dev)
         sT2 = torch.empty(B, H, K, V, dtype=torch.float32, device=dev)
 
         def fused():
-            qq, kk, vv, gg, bb = gdkvm_b200.qkvgb_project(x, w, None, H, K, V)
+            qq, kk, vv, gg, bb = gdkvm_b200.qkvgb_project(x, w, bias, H, K, V)
             gdkvm_b200.gdr_lkva_out(qq, kk, vv, gg, bb, o2, sT2, None, S0, C, 0)
 
         def unfused():
             with torch.no_grad():
-                qq, kk, vv, gg, bb = gdkvm_b200.qkvgb_project_reference(x, w, None, H, K, V)
+                qq, kk, vv, gg, bb = gdkvm_b200.qkvgb_project_reference(x, w, bias, H, K, V)
             gdkvm_b200.gdr_lkva_out(qq, kk, vv, gg, bb, o2, sT2, None, S0, C, 0)
 
         def norm_then_op():
             gdkvm_b200.gdr_lkva_out(gdkvm_b200.l2norm(q), gdkvm_b200.l2norm(k), v, g, beta, o2, sT2, None, S0, C, 0)
 
-        ms_p, _, _ = time_for(lambda: gdkvm_b200.qkvgb_project(x, w, None, H, K, V), args.extra_seconds / 2)
+        ms_p, _, _ = time_for(lambda: gdkvm_b200.qkvgb_project(x, w, bias, H, K, V), args.extra_seconds / 2)
         ms_f, st_f, win_f = time_for(fused, args.extra_seconds)
         ms_u, _, _ = time_for(unfused, args.extra_seconds / 2)
         ms_n, _, _ = time_for(norm_then_op, args.extra_seconds / 2)
@@ -395,13 +396,23 @@ def run_extras(args, dev, sampler, main_inputs, main_ms):
         ab_p = R * D * 2 + N * D * 2 + R * H * ((2 * K + V) * 2 + 8)          # features + weight read, op operands written
         peak, _ = measured_peak_gbs()
         tf = 2.0 * R * N * D / (ms_p * 1e-3) / 1e12
+        # 90 % of this kernel's traffic is WRITES, and a write-only stream does not reach the copy peak on this part: measure what a
+        # library fill of the same size reaches (torch fill_ = a plain store loop) and report the fraction of that as well
+        wbytes = R * H * ((2 * K + V) * 2 + 8)
+        scratch = torch.empty(wbytes // 2, dtype=torch.bfloat16, device=dev)
+        ms_w, _, _ = time_for(lambda: scratch.fill_(1.0), args.extra_seconds / 4)
+        del scratch
+        write_peak = wbytes / (ms_w * 1e-3) / 1e9
         return {"ms_per_step": ms_f, "steps": st_f, "value": B * W1["frames"] / (ms_f * 1e-3), "unit": UNIT,
                 "projection_kernel_ms": ms_p, "projection_roofline": {"bound": "hbm", "achieved": ab_p / (ms_p * 1e-3) / 1e9, "peak": peak,
                                                                       "unit": "GB/s", "frac": ab_p / (ms_p * 1e-3) / 1e9 / peak,
-                                                                      "algorithmic_bytes_per_step": ab_p, "TFLOPs": tf},
+                                                                      "algorithmic_bytes_per_step": ab_p, "TFLOPs": tf,
+                                                                      "write_only": {"bytes_written_per_step": wbytes, "fill_ms_same_bytes": ms_w,
+                                                                                     "fill_GBps": write_peak,
+                                                                                     "frac_of_fill": wbytes / (ms_p * 1e-3) / 1e9 / write_peak}},
                 "unfused_library_route_ms": ms_u, "speedup_over_unfused": ms_u / ms_f, "l2norm_x2_plus_op_ms": ms_n,
                 "clocks": sampler.window(*win_f) if sampler is not None else None,
-                "note": "features [64, 6272, 256] bf16 -> q,k,v,g,beta (N = 3088 columns) -> op. fused = qkvgb_proj_kernel (tcgen05 GEMM, "
+                "note": "features [64, 6272, 256] bf16 + bias -> q,k,v,g,beta (N = 3088 columns) -> op. fused = qkvgb_proj_kernel (tcgen05 GEMM, "
                         "L2-norm / sigmoid / logsigmoid epilogue) + op; unfused = torch linear (cuBLAS) + split + normalise + activations + op; "
                         "l2norm_x2_plus_op = the round-1 prologue (two normalisation passes over given q, k, no GEMM)"}
 

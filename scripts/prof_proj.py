@@ -7,6 +7,7 @@ dev = torch.device("cuda", 0)
 gen = torch.Generator(device=dev).manual_seed(2)
 x = torch.randn(64 * 6272, 256, generator=gen, device=dev).bfloat16()
 w = (torch.randn(8 * 384 + 16, 256, generator=gen, device=dev) / 16).bfloat16()
+b = 0.1 * torch.randn(8 * 384 + 16, generator=gen, device=dev)
 for _ in range(3):
-    gdkvm_b200.qkvgb_project(x, w, None, 8, 64, 256)
+    gdkvm_b200.qkvgb_project(x, w, b, 8, 64, 256)
 torch.cuda.synchronize()

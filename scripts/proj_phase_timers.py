@@ -24,7 +24,8 @@ gdkvm_b200.qkvgb_project(x, w, b, 8, 64, 256)
 lib.gdkvm_debug_proj_cycles(buf, 32)          # reset after the warm-up
 gdkvm_b200.qkvgb_project(x, w, b, 8, 64, 256)
 lib.gdkvm_debug_proj_cycles(buf, 32)
-tiles = -(-(R // 128) // 148) * 13            # column tiles CTA 0 went through
+bm = 128 if os.environ.get("GDKVM_PROJ_TILE_ROWS") == "128" else 256     # the library picks 256-row tiles at this size
+tiles = -(-(-(-R // bm)) // 148) * (13 if bm == 128 else 25)            # output tiles CTA 0 went through
 names = {0: "wait: accumulators of the tile complete", 1: "TMEM load (64 columns)", 2: "bias, sum of squares, rsqrt", 3: "wait: staging tile read by the last store",
          4: "scale, pack, staging writes", 5: "proxy fence + warp sync", 6: "bulk store issued", 16: "issuer wait: feature block", 17: "issuer wait: accumulator free",
          18: "issuer wait: weight k-block landed", 19: "issuer: four MMAs + commit"}
