@@ -177,9 +177,43 @@ def test_backward_and_projection_are_bit_deterministic(op):
     gen = torch.Generator(device="cuda").manual_seed(802)
     x = torch.randn(148 * 128 * 3 + 77, 256, generator=gen, device="cuda").bfloat16()
     w = (torch.randn(8 * 384 + 16, 256, generator=gen, device="cuda") / 16).bfloat16()
-    pref = op.qkvgb_project(x, w, None, 8, 64, 256)
-    for _ in range(9):
-        for a, b in zip(op.qkvgb_project(x, w, None, 8, 64, 256), pref):
+    bias = torch.randn(8 * 384 + 16, generator=gen, device="cuda")           # staged through shared memory by the producer warp
+    for bb in (None, bias):
+        pref = op.qkvgb_project(x, w, bb, 8, 64, 256)
+        for _ in range(9):
+            for a, b in zip(op.qkvgb_project(x, w, bb, 8, 64, 256), pref):
+                assert torch.equal(a, b)
+
+
+def test_training_step_inside_a_cuda_graph(op):
+    """Projection -> training forward -> backward captured into ONE CUDA graph and replayed on new data: none of the three
+    launches synchronises or allocates outside the stream (the backward's and the segment scheme's scratch become allocation
+    nodes), and the replays reproduce the eager results bit for bit."""
+    H, V, D = 8, 256, 256
+    gen = torch.Generator(device="cuda").manual_seed(901)
+    w = (torch.randn(H * (128 + V) + 2 * H, D, generator=gen, device="cuda") / D ** 0.5).bfloat16()
+    bias = 0.1 * torch.randn(w.shape[0], generator=gen, device="cuda")
+    bias[-2 * H:-H] += 3.0
+    xs = [torch.randn(20, 5 * 64 + 11, D, generator=gen, device="cuda").bfloat16() for _ in range(3)]      # 160 chains: cut into segments
+    do = torch.randn(20, 5 * 64 + 11, H, V, generator=gen, device="cuda").bfloat16()
+    dsT = torch.randn(20, H, 64, V, generator=gen, device="cuda")
+
+    def step(x):
+        q, k, v, g, beta = op.qkvgb_project(x, w, bias, H, 64, V)
+        o, sT, cs = torch.ops.gdkvm.gdr_lkva_train(q, k, v, g, beta, None, None, 0)
+        return (o, sT) + tuple(torch.ops.gdkvm.gdr_lkva_bwd(q, k, v, g, beta, cs, do, dsT, 0.125, False, None, 0))
+
+    eager = [[t.clone() for t in step(x) if t is not None] for x in xs]
+    xin = xs[0].clone()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = [t for t in step(xin) if t is not None]
+    for x, ref in zip(xs[::-1], eager[::-1]):
+        xin.copy_(x)
+        graph.replay()
+        torch.cuda.synchronize()
+        for a, b in zip(outs, ref):
             assert torch.equal(a, b)
 
 
