@@ -115,3 +115,16 @@ def test_projection_full_size_properties(op):
         for name, a, r in zip(("q", "k", "v", "g", "beta"), (q, k, v, g, beta), ref):
             tol = 2.0 ** -8 * max(1.0, float(r.abs().max())) if name in ("q", "k", "v") else 2e-4
             assert float((a[sl].float().cpu() - r).abs().max()) <= tol, (name, r0)
+
+
+def test_projection_tile_shapes_agree_bit_for_bit(op, monkeypatch):
+    """128-row and 256-row tiles run the same MMA sequence per output element (fp32 accumulation over the k-blocks in the same
+    order) and the same epilogue arithmetic: identical bits, with and without a bias, ragged last block included."""
+    x, w, b = _make((1500,), 256, 8, 256, 77, True)
+    for bias in (None, b.cuda()):
+        outs = {}
+        for rows in ("128", "256"):
+            monkeypatch.setenv("GDKVM_PROJ_TILE_ROWS", rows)
+            outs[rows] = op.qkvgb_project(x.cuda(), w.cuda(), bias, 8, 64, 256)
+        for name, a, c in zip(("q", "k", "v", "g", "beta"), outs["128"], outs["256"]):
+            assert torch.equal(a, c), name
