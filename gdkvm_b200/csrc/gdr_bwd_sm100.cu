@@ -37,6 +37,10 @@ using sm100::sw128_offset;
 using sm100::pack_bf16;
 
 constexpr int kBwdThreads = 512;                 // 16 warps: 4 (row tiles) x 4 (column groups)
+#ifndef GDKVM_BWD_UNROLL
+#define GDKVM_BWD_UNROLL 1
+#endif
+constexpr int kBwdUnroll = GDKVM_BWD_UNROLL;      // k-loop unrolling of the warp GEMMs (experiment knob)
 constexpr int LD64 = 72, LD128 = 136;            // padded leading dimensions (elements): rows 16-byte aligned, ldmatrix conflict-free
 constexpr uint32_t SZ64 = 64 * LD64 * 2;         // 64 x 64 bf16 tile
 constexpr uint32_t SZ128 = 64 * LD128 * 2;       // 64 x 128 bf16 tile
@@ -107,7 +111,7 @@ __device__ __forceinline__ void wgemm(float (&acc)[NT][4], uint32_t A, int m0, u
     constexpr bool kPipe = false;
 #endif
     if constexpr (!kPipe) {            // NT = 4: four independent MMAs per A fragment already; a second register set would spill
-#pragma unroll 1
+#pragma unroll kBwdUnroll
         for (int k = k0; k < k1; k += 16) {
             load(k, a0, b0);
             mmas(a0, b0);
@@ -137,7 +141,7 @@ __device__ __forceinline__ void wgemm_pair(float (&acc1)[2][4], float (&acc2)[2]
                                  : B1 + (uint32_t)(((n0 + (lane & 7) + 8 * (lane >> 4)) * LDB1 + 8 * ((lane >> 3) & 1)) * 2);
     const uint32_t b2_lane = TB2 ? B2 + (uint32_t)((((lane & 7) + 8 * ((lane >> 3) & 1)) * LDB2 + n0 + 8 * (lane >> 4)) * 2)
                                  : B2 + (uint32_t)(((n0 + (lane & 7) + 8 * (lane >> 4)) * LDB2 + 8 * ((lane >> 3) & 1)) * 2);
-#pragma unroll 1
+#pragma unroll kBwdUnroll
     for (int k = k0; k < k1; k += 16) {
         uint32_t a[4], b1[4], b2[4];
         ldsm4(a, a_lane + (uint32_t)(k * 2));
