@@ -175,7 +175,7 @@ int gdkvm_gdr_fwd_train(const GdkvmGdrParams* params, void* chunk_states, void* 
     if (params->flags & GDKVM_FLAG_FORCE_RECURRENT) return GDKVM_ERR_UNSUPPORTED;
     if (!gdkvm::chunked_supports(*params)) return params->T == 0 ? GDKVM_ERR_SHAPE : GDKVM_ERR_UNSUPPORTED;
     if (chunk_states == nullptr) return GDKVM_ERR_NULL;
-    if (reinterpret_cast<uintptr_t>(chunk_states) & 15u) return GDKVM_ERR_ALIGN;
+    if (reinterpret_cast<uintptr_t>(chunk_states) & 31u) return GDKVM_ERR_ALIGN;          // written with 256-bit stores
     bool sm100 = false;
     int ce = gdkvm::device_is_sm100(&sm100);
     if (ce != 0) { gdkvm::tl_last_cuda_error = ce; return GDKVM_ERR_CUDA; }
@@ -196,7 +196,7 @@ int gdkvm_gdr_fwd_train_varlen(const GdkvmGdrParams* params, const void* cu_seql
     if (rc != GDKVM_OK) return rc;
     if (params->B != 1 || n_seqs < 1 || (cu_seqlens_bytes != 4 && cu_seqlens_bytes != 8)) return GDKVM_ERR_SHAPE;
     if (cu_seqlens == nullptr || chunk_states == nullptr) return GDKVM_ERR_NULL;
-    if (reinterpret_cast<uintptr_t>(cu_seqlens) % (uintptr_t)cu_seqlens_bytes != 0 || (reinterpret_cast<uintptr_t>(chunk_states) & 15u)) return GDKVM_ERR_ALIGN;
+    if (reinterpret_cast<uintptr_t>(cu_seqlens) % (uintptr_t)cu_seqlens_bytes != 0 || (reinterpret_cast<uintptr_t>(chunk_states) & 31u)) return GDKVM_ERR_ALIGN;
     if ((int64_t)n_seqs * params->H > 0x3fffffff) return GDKVM_ERR_SHAPE;
     if (params->flags & GDKVM_FLAG_FORCE_RECURRENT) return GDKVM_ERR_UNSUPPORTED;
     if (params->T == 0) return GDKVM_ERR_SHAPE;

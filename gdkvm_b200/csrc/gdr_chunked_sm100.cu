@@ -744,9 +744,13 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                             const int m = kVar ? n : (int)s_info[4] + n;
                             if ((kVar || m < nc_chain) && vcol < V) {
                                 const int64_t blk = kVar ? ((int64_t)s_info[8] + n) * p.H + s_info[3] : (int64_t)s_info[1] * nc_chain + m;
-                                uint4* dst = reinterpret_cast<uint4*>(sdump + (blk * V + vcol) * 64);
+                                // 256-bit stores: a whole 32-byte sector per lane and instruction (1.49 -> 1.36 ms for the training
+                                // forward at configs[1] against 16-byte stores, profiles/r4y_state_dump_256bit_stores_ab.log)
+                                uint8_t* dst = reinterpret_cast<uint8_t*>(sdump + (blk * V + vcol) * 64);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                                for (int j = 0; j < 4; ++j)
+                                    st_global_v8(dst + 32 * j, pk[8 * j], pk[8 * j + 1], pk[8 * j + 2], pk[8 * j + 3], pk[8 * j + 4], pk[8 * j + 5],
+                                                 pk[8 * j + 6], pk[8 * j + 7]);
                             }
                         }
                         if (pre != 1.f) {      // slow path only

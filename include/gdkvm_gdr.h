@@ -173,8 +173,8 @@ int gdkvm_l2norm_fwd(const void* x, void* y, int64_t rows, int32_t D, int64_t x_
  * gdkvm_gdr_fwd_train = gdkvm_gdr_fwd on the tcgen05 chunk kernel (bf16 I/O, K = 64, V in {64, 128, 256}; anything else returns
  * GDKVM_ERR_UNSUPPORTED -- there is no slow training path) which ALSO writes the bf16 state at the start of every 64-token
  * chunk into `chunk_states`, a caller-owned device buffer of gdkvm_gdr_chunk_states_bytes(B, T, H, K, V) bytes laid out
- * [B*H][ceil(T/64)][V][K].  The token stream is tiled flat in 64-token chunks (frame_tokens is ignored; results equal
- * within the op's tolerance).
+ * [B*H][ceil(T/64)][V][K], 32-byte aligned (GDKVM_ERR_ALIGN otherwise: it is written with 256-bit stores).  The token stream is
+ * tiled flat in 64-token chunks (frame_tokens is ignored; results equal within the op's tolerance).
  */
 int gdkvm_gdr_fwd_train(const GdkvmGdrParams* params, void* chunk_states, void* cuda_stream);
 int64_t gdkvm_gdr_chunk_states_bytes(int32_t B, int32_t T, int32_t H, int32_t K, int32_t V);
