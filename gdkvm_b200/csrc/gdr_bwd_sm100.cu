@@ -219,6 +219,21 @@ __device__ __forceinline__ void load_tile(uint8_t* smem, uint32_t saddr, const _
     }
 }
 
+// L2 prefetch of rows [0, valid) x COLS bf16 columns of a global tile, one 128-byte line per instruction: the cp.async loads
+// that follow a phase or two later then hit L2 instead of waiting for HBM (they are issued late because their shared-memory
+// tiles are still in use)
+#ifndef GDKVM_BWD_PREFETCH
+#define GDKVM_BWD_PREFETCH 1     // 7.88 -> 7.71 ms at configs[1] (profiles/r5d_bwd_l2_prefetch_ab.log)
+#endif
+template <int COLS>
+__device__ __forceinline__ void prefetch_tile_l2(const __nv_bfloat16* src, int64_t row_stride, int valid, int tid) {
+    constexpr int lpr = (COLS * 2 + 127) / 128;      // lines per row
+    for (int idx = tid; idx < valid * lpr; idx += kBwdThreads) {
+        const int r = idx / lpr, l = idx - r * lpr;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (int64_t)r * row_stride + l * 64));
+    }
+}
+
 // ---- optional phase timers (-DGDKVM_BWD_TIMERS, scripts/bwd_phase_timers.py): cycles of CTA 0 between consecutive barriers ----
 #ifdef GDKVM_BWD_TIMERS
 __device__ unsigned long long g_bwd_cycles[64];
@@ -394,6 +409,27 @@ __global__ void __launch_bounds__(kBwdThreads, 1) gdr_bwd_kernel(const GdkvmGdrB
         cp_async_wait_all();
         SYNC(0);
         const float gamma = sE[63];
+        if (GDKVM_BWD_PREFETCH) {
+            // this chunk's second value half and the next chunk (one step back in time) towards L2, spread over the CTA
+            if (NH > 1) {
+                prefetch_tile_l2<128>(vg + (int64_t)t0 * p.v_stride[1] + 128, p.v_stride[1], valid, tid);
+                prefetch_tile_l2<128>(dog + (int64_t)t0 * p.do_stride[1] + 128, p.do_stride[1], valid, tid);
+                prefetch_tile_l2<64>(sc_ptr + 128 * 64, 64, 128, tid);
+            }
+            if (c > c_lo) {
+                const int64_t tp = (int64_t)(c - 1) << 6;
+                prefetch_tile_l2<64>(kg + tp * p.k_stride[1], p.k_stride[1], 64, tid);
+                prefetch_tile_l2<64>(qg + tp * p.q_stride[1], p.q_stride[1], 64, tid);
+                if (V >= 128) {
+                    prefetch_tile_l2<128>(vg + tp * p.v_stride[1], p.v_stride[1], 64, tid);
+                    prefetch_tile_l2<128>(dog + tp * p.do_stride[1], p.do_stride[1], 64, tid);
+                } else {
+                    prefetch_tile_l2<64>(vg + tp * p.v_stride[1], p.v_stride[1], 64, tid);
+                    prefetch_tile_l2<64>(dog + tp * p.do_stride[1], p.do_stride[1], 64, tid);
+                }
+                prefetch_tile_l2<64>(sg + (cs_blk0 + (int64_t)(c - 1) * cs_blk_stride) * V * 64, 64, min(128, V), tid);
+            }
+        }
 
         // ---- K K^T, Q K^T -> A (fp16, the solve's layout), K K^T D (bf16), P' = scale tril(Q K^T D) (bf16); Qe = scale e Q ----
         {
