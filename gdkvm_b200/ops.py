@@ -531,7 +531,10 @@ def _qkvgb_project_cuda(x, weight, bias, heads, d_k, d_v, eps=1e-6):
     p.x, p.w, p.bias = x2.data_ptr(), w.data_ptr(), (bias.data_ptr() if bias is not None else None)
     p.q, p.k, p.v, p.g, p.beta = q.data_ptr(), k.data_ptr(), v.data_ptr(), g.data_ptr(), beta.data_ptr()
     p.R, p.x_row_stride, p.D, p.H, p.K, p.V, p.eps = R, x2.stride(0), D, H, K, V, float(eps)
-    p.flags = {"": 0, "128": 1, "256": 2}[os.environ.get("GDKVM_PROJ_TILE_ROWS", "")]      # tests / A-B runs: force a tile shape
+    rows = os.environ.get("GDKVM_PROJ_TILE_ROWS", "")                                      # tests / A-B runs: force a tile shape
+    if rows not in ("", "128", "256"):
+        raise ValueError(f"GDKVM_PROJ_TILE_ROWS must be 128 or 256 (got {rows!r})")
+    p.flags = {"": 0, "128": 1, "256": 2}[rows]
     lib = _cabi.load()
     with torch.cuda.device(dev):
         rc = lib.gdkvm_qkvgb_project_fwd(ctypes.byref(p), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
