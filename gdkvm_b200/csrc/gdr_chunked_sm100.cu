@@ -720,17 +720,23 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 PT(17, tid == 256, n);   // wait: state update of chunk n-1
                 {   // S_n = post_{n-1} * accumulator;  Sb = bf16(S_n) (operand copy);  accumulator <- pre_n * S_n
                     const float post = n >= 1 ? sPost[(n - 1) & 3] : 1.f, pre = sPre[n & 3];
+#ifdef GDKVM_ABLATE_DECAY      // measurement only (wrong results): what a deferred decay of the state accumulator could save
+                    const bool rescale = false;
+#else
                     const bool rescale = pre != 1.f || post != 1.f;
+#endif
                     if (!ABL(5)) {   // both 32-column halves in flight at once (one TMEM load latency instead of two)
                         uint32_t ra[32], rb[32], pk[32];
                         tmem_ld32(lane_addr + kColS + hh * 64, ra);
                         tmem_ld32(lane_addr + kColS + hh * 64 + 32, rb);
                         tmem_wait_ld();
+#ifndef GDKVM_ABLATE_DECAY
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             ra[j] = __float_as_uint(__uint_as_float(ra[j]) * post);
                             rb[j] = __float_as_uint(__uint_as_float(rb[j]) * post);
                         }
+#endif
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             pk[j] = pack_bf16(__uint_as_float(ra[2 * j]), __uint_as_float(ra[2 * j + 1]));
