@@ -732,3 +732,16 @@ def test_full_size_long_clips_two_chained_calls_vs_oracle(op, c_oracle):
     oa2, sa2 = op.gdr_lkva(q[:, :cut], k[:, :cut], v[:, :cut], g[:, :cut], beta[:, :cut], None, S0, True, C, FRAME)
     ob2, sb2 = op.gdr_lkva(q[:, cut:], k[:, cut:], v[:, cut:], g[:, cut:], beta[:, cut:], None, sa2, True, C, FRAME)
     assert torch.equal(torch.cat([oa2, ob2], 1), o1) and torch.equal(sb2, s1)            # same chunking: bit-identical
+
+
+def test_recurrent_kernel_two_columns_per_thread(op):
+    """With >= 444 CTAs and d_v > 128 the fp32 kernel gives every thread two value columns (x and x + 128): a ragged second
+    column block (d_v = 192), a full one (d_v = 256), fp32 and bf16 I/O, against the oracle -- and equal to the one-column
+    layout of the same arithmetic (a batch too small for the switch) bit for bit."""
+    for V, dtype in ((192, torch.float32), (256, torch.float32), (256, torch.bfloat16)):
+        q, k, v, g, beta, S0 = make_inputs(60, 37, 8, 64, V, seed=900 + V, dtype=dtype)
+        o_ref, s_ref = gdr_recurrent_ref(q, k, v, g, beta, None, S0)
+        o, sT = _run(op, q, k, v, g, beta, S0, flags=RECURRENT)
+        assert max_rel_err(o, o_ref) <= (1e-5 if dtype == torch.float32 else TOL[dtype]) and max_rel_err(sT, s_ref) <= 1e-5
+        o1, s1 = _run(op, q[:3], k[:3], v[:3], g[:3], beta[:3], S0[:3], flags=RECURRENT)          # 24 chains: one column per thread
+        assert torch.equal(o1, o[:3]) and torch.equal(s1, sT[:3])
