@@ -570,6 +570,21 @@ def test_second_device_in_one_process(op):
         torch.cuda.synchronize(dev)
         outs.append((o.cpu(), sT.cpu()))
     assert all(torch.equal(outs[0][0], x[0]) and torch.equal(outs[0][1], x[1]) for x in outs[1:])
+    # the same for the training forward, the backward kernel and both tile shapes of the projection kernel
+    gen = torch.Generator().manual_seed(92)
+    do, dsT = torch.randn(2, 5 * 64, 2, 256, generator=gen).bfloat16(), torch.randn(2, 2, 64, 256, generator=gen)
+    x = torch.randn(300, 128, generator=gen).bfloat16()
+    w = (torch.randn(2 * (128 + 64) + 4, 128, generator=gen) / 11).bfloat16()
+    res = []
+    for dev in ("cuda:1", "cuda:0", "cuda:1"):
+        t = [y.to(dev) for y in (q, k, v, g, beta, S0, do, dsT, x, w)]
+        o, sT, cs = torch.ops.gdkvm.gdr_lkva_train(*t[:5], None, t[5], 0)
+        grads = torch.ops.gdkvm.gdr_lkva_bwd(*t[:5], cs, t[6], t[7], 0.125, True, None, 0)
+        proj = op.qkvgb_project(t[8], t[9], None, 2, 64, 64)
+        torch.cuda.synchronize(dev)
+        res.append([y.cpu() for y in (o, sT, *grads, *proj)])
+    for other in res[1:]:
+        assert all(torch.equal(a, b) for a, b in zip(res[0], other))
 
 
 def test_unforced_fallback_warns_once_with_the_reason(op):
