@@ -133,6 +133,8 @@ enum Bar : int {
 // for chunks kTraceFirst + c (a steady-state window), which gives a cross-role timeline of CTA 0.
 __device__ unsigned long long g_phase_cycles[64];
 __device__ long long g_phase_trace[64][8];
+__device__ long long g_unit_marks[16];      // clock64 of CTA 0 at fixed points of a work unit (scripts/unit_marks.py)
+#define UM(i, cond) do { if (blockIdx.x == 0 && (cond)) g_unit_marks[i] = clock64(); } while (0)
 constexpr int kTraceFirst = 40;
 #define PT_DECL long long pt_prev = clock64();
 #define PT(slot, cond, chunk)                                                          \
@@ -148,6 +150,7 @@ constexpr int kTraceFirst = 40;
 #else
 #define PT_DECL
 #define PT(slot, cond, chunk) do { } while (0)
+#define UM(i, cond) do { } while (0)
 #endif
 
 // ---- ablation switches (timing experiments only; results are wrong when any bit is set) ----
@@ -359,6 +362,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     volatile int* s_info = reinterpret_cast<volatile int*>(s_tmem + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    UM(0, tid == 0);                              // kernel entry
     // V = 64: one state warpgroup whose upper 64 TMEM lanes idle on zeros (the second value block of the V ring is never loaded)
     const int V = p.V, NH = V > 128 ? 2 : 1, VB = V >> 6;
     const uint32_t v_tile_bytes = V >= 128 ? 16384u : 8192u;
@@ -415,6 +419,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    UM(1, tid == 0);                              // setup done: barriers, zeroed tiles, TMEM allocated
     const uint32_t tmem = *s_tmem;
     // Chunks s_info[4] .. + NC - 1 of the chain; n below counts inside the segment.  NC is the same for every unit (a
     // kernel parameter, so every loop bound stays warp-uniform for the compiler); chunks past the end of the chain in
@@ -605,6 +610,8 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
             fence_proxy_async_smem();
             kbar();
             PT(6, tid == 0, n);   // T' conversion
+            if (n == 0) UM(3, tid == 0);          // K side of the unit's first chunk published
+            if (n == NC - 1) UM(4, tid == 0);     // K side of the unit's last chunk published
             if (tid == 0) mbar_arrive(&bars[kTpReady + st]);
         }
     } else if (warp < 16) {
@@ -641,6 +648,7 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                     tmem_st32(lane_addr + kColS + hh * 64 + half * 32, r);
                 }
                 tmem_wait_st();
+                UM(2, tid == 256);                    // initial state in TMEM
             }
             // drain the readout of chunk m: O^T accumulators in mma-fragment layout (16x256b TMEM loads) -> * scale e_i
             // -> bf16 pairs -> stmatrix.trans into the 128B-swizzled staging tile [2][tok][64] -> TMA store
@@ -810,9 +818,12 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 PT(21, tid == 256, n);   // Vnb pass
                 if (n + 1 < NC) wt_operand(n + 1);
             }
+            UM(6, tid == 256);                        // last Vnb pass done
             readout(NC - 1);
+            UM(7, tid == 256);                        // last readout drained
             mbar_wait_inl(&bars[kSReady + hh], (uint32_t)(NC - 1) & 1u);
             tc_fence_after_sync();
+            UM(8, tid == 256);                        // last state update complete
             const int chain = U_CHAIN, seg = U_SEG;
             const bool last_seg = s_info[7] != 0;
             float* sT = last_seg ? p.final_state : xstate;       // the caller's final state | hand-off to the next segment
@@ -833,7 +844,9 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
                 named_bar_sync(bar_id, 128);
                 if (stid == 0) st_release_gpu(xsync + 1 + chain * 2 + hh, seg + 1);
             }
+            UM(9, tid == 256);                        // final state stored / handed over
             if (stid == 0) tma_store_wait_all0();
+            UM(10, tid == 256);                       // readout stores complete
             tc_fence_before_sync();
         }
     } else {
@@ -947,7 +960,9 @@ gdr_chunk_kernel(const __grid_constant__ CUtensorMap mq, const __grid_constant__
     // ---- teardown ----
     tc_fence_before_sync();
     __syncthreads();
+    UM(11, tid == 0);
     if (warp == 16) tmem_dealloc(tmem, kTmemCols);
+    UM(12, tid == 512);                           // warp 16: TMEM released
 }
 
 bool mult16(int64_t elems) { return (elems * 2) % 16 == 0; }
@@ -1070,6 +1085,13 @@ extern "C" int gdkvm_debug_phase_cycles(unsigned long long* out, int n) {
     for (int i = 0; i < n && i < 64; ++i) out[i] = h[i];
     unsigned long long z[64] = {0};
     cudaMemcpyToSymbol(gdkvm::g_phase_cycles, z, sizeof z);
+    return 0;
+}
+extern "C" int gdkvm_debug_unit_marks(long long* out, int n) {
+    long long h[16];
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (cudaMemcpyFromSymbol(h, gdkvm::g_unit_marks, sizeof h) != cudaSuccess) return -1;
+    for (int i = 0; i < n && i < 16; ++i) out[i] = h[i];
     return 0;
 }
 extern "C" int gdkvm_debug_phase_trace(long long* out, int n) {   // out[64][8]
