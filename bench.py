@@ -686,6 +686,12 @@ def main():
     plan = gdkvm_b200.plan(q, k, v, g, beta, frame_tokens=C, flags=args.flags)
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     segments = gdkvm_b200.plan_segments(q, k, v, g, beta, frame_tokens=C, flags=args.flags, sm_count=sms)
+    units = gdkvm_b200.plan_units(q, k, v, g, beta, frame_tokens=C, flags=args.flags, sm_count=sms)
+    if units["mixed"]:
+        seg_text = (f"mixed plan: {units['uncut_clips']} clips uncut, {units['cut_clips']} clips in {units['segments']} time segments: "
+                    f"{units['units']} work units on {sms} SMs")
+    else:
+        seg_text = f"{segments} per (clip, head) chain: {B * H * segments} work units on {sms} SMs"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(), "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
                 "kernel": "gdr_chunk_kernel (tcgen05)" if plan == 1 else "gdr_recurrent_kernel (fp32 CUDA cores)",
@@ -742,7 +748,7 @@ def main():
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": W["name"], "clips_per_gpu": B, "frames": W["frames"], "frame_tokens": C, "heads": H,
                    "d_k": K, "d_v": V, "tokens_per_clip": T, "flags": args.flags, "kernel": kernel,
-                   "time_segments": f"{segments} per (clip, head) chain: {B * H * segments} work units on {sms} SMs",
+                   "time_segments": seg_text,
                    "arithmetic": "bf16 q/k/v/o and tensor-core operands, fp32 state/accumulators/gates",
                    "l2": "inputs+outputs per step (%.1f GB) exceed the 126 MB L2; no flush needed" % (abytes / 1e9),
                    "sharding": "clips x heads across ranks, no collective on the hot path"},

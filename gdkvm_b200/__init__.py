@@ -4,7 +4,7 @@ Only the hot path of wangrui2025/GDKVM named by BASELINE.json ``north_star`` liv
 ``csrc/`` (hand-written sm_100a CUDA behind the C ABI of ``include/gdkvm_gdr.h``) and the
 host-side mirror of the reference memory module's call surface.
 """
-from .ops import chunk_gated_delta_rule, gdr_lkva, gdr_lkva_out, gdr_lkva_varlen, gdr_lkva_varlen_out, check_inputs, l2norm, launch_count, plan, plan_reason, plan_segments, qkvgb_project, qkvgb_project_reference, train_unsupported_reason  # noqa: F401
+from .ops import chunk_gated_delta_rule, gdr_lkva, gdr_lkva_out, gdr_lkva_varlen, gdr_lkva_varlen_out, check_inputs, l2norm, launch_count, plan, plan_reason, plan_segments, plan_units, qkvgb_project, qkvgb_project_reference, train_unsupported_reason  # noqa: F401
 from .memory import GDRMemory  # noqa: F401
 from .model import GDKVMSkeleton  # noqa: F401
 from ._cabi import FLAG_FLAT_CHUNKS, FLAG_FORCE_CHUNKED, FLAG_FORCE_RECURRENT, FLAG_FRAME_CHUNKS, FLAG_SEGMENTS  # noqa: F401

@@ -19,7 +19,7 @@ def FLAG_SEGMENTS(n: int) -> int:
 
 EXPORTED_SYMBOLS = (
     "gdkvm_abi_version", "gdkvm_strerror", "gdkvm_last_cuda_error",
-    "gdkvm_gdr_fwd", "gdkvm_gdr_fwd_varlen", "gdkvm_gdr_plan", "gdkvm_gdr_plan_segments", "gdkvm_gdr_plan_reason",
+    "gdkvm_gdr_fwd", "gdkvm_gdr_fwd_varlen", "gdkvm_gdr_plan", "gdkvm_gdr_plan_segments", "gdkvm_gdr_plan_units", "gdkvm_gdr_plan_reason",
     "gdkvm_launch_count", "gdkvm_l2norm_fwd", "gdkvm_gdr_fwd_train", "gdkvm_gdr_chunk_states_bytes", "gdkvm_gdr_bwd",
     "gdkvm_gdr_fwd_train_varlen", "gdkvm_gdr_chunk_states_bytes_varlen",
     "gdkvm_qkvgb_project_fwd",
@@ -96,6 +96,8 @@ def load() -> ctypes.CDLL:
             lib.gdkvm_gdr_plan.argtypes = [ctypes.POINTER(GdkvmGdrParams)]
             lib.gdkvm_gdr_plan_segments.restype = ctypes.c_int
             lib.gdkvm_gdr_plan_segments.argtypes = [ctypes.POINTER(GdkvmGdrParams), ctypes.c_int]
+            lib.gdkvm_gdr_plan_units.restype = ctypes.c_int
+            lib.gdkvm_gdr_plan_units.argtypes = [ctypes.POINTER(GdkvmGdrParams), ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]
             lib.gdkvm_gdr_plan_reason.restype = ctypes.c_char_p
             lib.gdkvm_gdr_plan_reason.argtypes = [ctypes.POINTER(GdkvmGdrParams)]
             lib.gdkvm_launch_count.restype = ctypes.c_uint64

@@ -114,6 +114,20 @@ int gdkvm_gdr_plan_segments(const GdkvmGdrParams* params, int sm_count) {
     return gdkvm::chunked_segments(*params, sm_count);
 }
 
+int gdkvm_gdr_plan_units(const GdkvmGdrParams* params, int sm_count, int32_t out[4]) {
+    const int rc = gdkvm::validate(params);
+    if (rc != GDKVM_OK) return rc;
+    if (out == nullptr) return GDKVM_ERR_NULL;
+    if (params->T == 0 || gdkvm::pick(params) != 1) {          // not the chunk kernel: one unit per (clip, head) chain
+        out[0] = params->B * params->H; out[1] = params->B; out[2] = 0; out[3] = 1;
+        return 0;
+    }
+    int o[4];
+    const int mixed = gdkvm::chunked_plan_units(*params, sm_count, o);
+    for (int i = 0; i < 4; ++i) out[i] = o[i];
+    return mixed;
+}
+
 int gdkvm_l2norm_fwd(const void* x, void* y, int64_t rows, int32_t D, int64_t x_row_stride, int64_t y_row_stride,
                      int32_t dtype, float eps, void* cuda_stream) {
     if (rows < 0 || (D != 32 && D != 64 && D != 128 && D != 256)) return GDKVM_ERR_SHAPE;

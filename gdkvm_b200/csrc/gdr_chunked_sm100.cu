@@ -1014,6 +1014,60 @@ int pick_segments(int chains, int nc, int sms) {
     return best;
 }
 
+// Mixed plan for a batch of equal-length chains that fills more than one wave: whole waves of UNCUT chains (a unit boundary costs
+// ~2.85 chunk periods -- scripts/unit_overhead.py -- so every cut is paid for), and only the clips left over for the ragged last
+// wave are cut, into about one unit per SM.  Ticket order: the first segments of the cut clips, the uncut clips, then the later
+// segments of the cut clips level by level (a predecessor always holds a smaller ticket and has long finished).  configs[1]:
+// 55 clips uncut + 9 clips in two segments = 4 units per SM instead of 7.  Returns the simulated makespan (chunk periods) and the
+// plan, or a negative value when there is nothing to gain over the uniform plan `uniform_t`.
+struct MixedPlan { int uncut_clips = 0, cut_clips = 0, nseg = 1, seg_chunks = 0; };
+
+double simulate_mixed(int H, int nc, int sms, const MixedPlan& m) {
+    std::priority_queue<double, std::vector<double>, std::greater<double>> sm_free;
+    for (int i = 0; i < sms; ++i) sm_free.push(0.0);
+    std::vector<double> done((size_t)m.cut_clips * H, 0.0);
+    double makespan = 0.0;
+    auto run = [&](double len, double pred) {
+        const double t0 = sm_free.top();
+        sm_free.pop();
+        const double end = std::max(t0, pred) + len;
+        sm_free.push(end);
+        makespan = std::max(makespan, end);
+        return end;
+    };
+    const int nsegs = (nc + m.seg_chunks - 1) / m.seg_chunks;
+    for (int c = 0; c < m.cut_clips * H; ++c) done[(size_t)c] = run(std::min(m.seg_chunks, nc) + kUnitOverhead, 0.0);
+    for (int c = 0; c < m.uncut_clips * H; ++c) run(nc + kUnitOverhead, 0.0);
+    for (int l = 1; l < nsegs; ++l)
+        for (int c = 0; c < m.cut_clips * H; ++c)
+            done[(size_t)c] = run(std::min(m.seg_chunks, nc - l * m.seg_chunks) + kUnitOverhead, done[(size_t)c]);
+    return makespan;
+}
+
+double pick_mixed(int B, int H, int nc, int sms, double uniform_t, MixedPlan* out) {
+    const int chains = B * H, waves = chains / sms;
+    if (waves < 1 || nc < 16 || (int64_t)chains * kMaxSegments > (1 << 16)) return -1.0;
+    MixedPlan best;
+    double best_t = -1.0;
+    // candidates: the clips of `waves` (or one fewer) whole waves stay uncut
+    for (int w = waves; w >= std::max(1, waves - 1); --w) {
+        MixedPlan m;
+        m.uncut_clips = std::min(B, (w * sms) / H);
+        m.cut_clips = B - m.uncut_clips;
+        if (m.cut_clips == 0) continue;
+        const int target = std::max(1, (int)((double)sms / (m.cut_clips * H) + 0.5));
+        for (int s = std::max(1, target - 1); s <= std::min({target + 1, kMaxSegments, nc / 8}); ++s) {
+            m.seg_chunks = (nc + s - 1) / s;
+            m.nseg = (nc + m.seg_chunks - 1) / m.seg_chunks;
+            const double t = simulate_mixed(H, nc, sms, m);
+            if (best_t < 0 || t < best_t) { best_t = t; best = m; }
+        }
+    }
+    if (best_t < 0 || best_t > uniform_t * 0.985) return -1.0;       // only for a real gain
+    *out = best;
+    return best_t;
+}
+
 // Per-device facts and resources, created on first use under one mutex: SM count, memory-pool support, the dynamic
 // shared-memory opt-in of both kernel instantiations (cudaFuncSetAttribute is per device/context, so a process that
 // drives several GPUs needs it on each), and a library-PRIVATE stream-ordered memory pool for the hand-off scratch of
@@ -1232,6 +1286,30 @@ __global__ void __launch_bounds__(256) gdr_units_kernel(const IdxT* __restrict__
     }
 }
 
+// Work-unit table of the mixed plan (pick_mixed): clips [0, uncut) whole, clips [uncut, B) in `nsegs` segments of `sc` chunks;
+// every clip has T tokens at packed offset clip * T.  Entry layout as in gdr_units_kernel.
+__global__ void __launch_bounds__(256) gdr_units_mixed_kernel(int B, int T, int uncut, int nsegs, int sc, int* __restrict__ utab,
+                                                              int* __restrict__ xsync, int sync_ints) {
+    const int cut = B - uncut, entries = cut + uncut + cut * (nsegs - 1);
+    for (int i = threadIdx.x; i < sync_ints; i += 256) xsync[i] = 0;          // ticket counter and hand-off flags (no separate memset)
+    for (int pos = threadIdx.x; pos < entries; pos += 256) {
+        int n, lvl, segs, size;
+        if (pos < cut) { n = uncut + pos; lvl = 0; segs = nsegs; size = sc; }
+        else if (pos < cut + uncut) { n = pos - cut; lvl = 0; segs = 1; size = (T + 63) >> 6; }
+        else { const int v = pos - cut - uncut; lvl = 1 + v / cut; n = uncut + v % cut; segs = nsegs; size = sc; }
+        const long long t0 = (long long)n * T;
+        const int first = lvl * size;
+        const long long rest = (long long)T - (long long)first * 64;
+        const bool last = lvl == segs - 1;
+        int* e = utab + kUnitInts * (1 + pos);
+        e[0] = n; e[1] = (int)(t0 + (long long)first * 64);
+        e[2] = last ? (int)rest : size * 64;
+        e[3] = last ? (int)((rest + 63) >> 6) : size;
+        e[4] = lvl; e[5] = last ? 1 : 0; e[6] = 0; e[7] = 0;
+    }
+    if (threadIdx.x == 0) utab[0] = entries;
+}
+
 }  // namespace
 
 int plan_time_segments(int chains, int chunks, int sms) { return pick_segments(chains, chunks, sms > 0 ? sms : 148); }
@@ -1245,6 +1323,82 @@ int library_scratch_alloc(void** ws, size_t bytes, cudaStream_t stream, int* sms
     const cudaError_t e = scratch_alloc(ws, bytes, dc, stream);
     if (e != cudaSuccess) (void)cudaGetLastError();
     return (int)e;
+}
+
+namespace {
+
+bool pick_mixed_cached(int B, int H, int nc, int sms, int uniform_seg_chunks, MixedPlan* out) {
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, int, int>, MixedPlan> cache;       // cut_clips == 0: the uniform plan stays
+    const auto key = std::make_tuple(B, H, nc, sms);
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        MixedPlan m;
+        const double tu = simulate_units(B * H, nc, sms, uniform_seg_chunks);
+        if (pick_mixed(B, H, nc, sms, tu, &m) < 0) m = MixedPlan();
+        if (cache.size() > 4096) cache.clear();
+        it = cache.emplace(key, m).first;
+    }
+    *out = it->second;
+    return out->cut_clips > 0;
+}
+
+// Whether an (inference) launch of this problem takes the mixed plan, and which.
+bool mixed_plan_for(const GdkvmGdrParams& p, int sms, MixedPlan* mp) {
+    const bool flat = p.frame_tokens <= 0 || (p.flags & GDKVM_FLAG_FLAT_CHUNKS) || (p.frame_tokens % 64 != 0 && !(p.flags & GDKVM_FLAG_FRAME_CHUNKS));
+    if (!flat || ((p.flags >> 8) & 0xfu) != 0 || p.B <= 1 || (int64_t)p.B * p.T >= ((int64_t)1 << 31)) return false;
+    if (p.q_stride[0] != (int64_t)p.T * p.q_stride[1] || p.k_stride[0] != (int64_t)p.T * p.k_stride[1] ||
+        p.v_stride[0] != (int64_t)p.T * p.v_stride[1] || p.o_stride[0] != (int64_t)p.T * p.o_stride[1] ||
+        p.g_stride[0] != (int64_t)p.T * p.g_stride[1] || p.beta_stride[0] != (int64_t)p.T * p.beta_stride[1])
+        return false;
+    const int nc = (p.T + 63) / 64, ns = pick_segments(p.B * p.H, nc, sms), sc = (nc + ns - 1) / ns;
+    return pick_mixed_cached(p.B, p.H, nc, sms, sc, mp);
+}
+
+// The batch as ONE packed token stream (clip n = rows n T .. (n + 1) T - 1) through the unit-table kernel with the mixed plan's table.
+int launch_chunked_mixed(const GdkvmGdrParams& p, const MixedPlan& mp, const DeviceCtx* dc, cudaStream_t stream) {
+    GdkvmGdrParams pp = p;
+    pp.B = 1;
+    pp.T = p.B * p.T;
+    CUtensorMap mq, mk, mv, mo;
+    const int me = make_maps(pp, pp.T, 1, &mq, &mk, &mv, &mo);
+    if (me != 0) return me;
+    const int H = p.H, V = p.V, chains = p.B * H;
+    const int entries = mp.cut_clips * mp.nseg + mp.uncut_clips;
+    const size_t state_bytes = (size_t)chains * 64 * V * sizeof(float);
+    const size_t sync_bytes = (((size_t)chains * 2 + 1) * sizeof(int) + 15) & ~(size_t)15;
+    const size_t tab_bytes = (size_t)kUnitInts * (1 + (size_t)entries) * sizeof(int);
+    void* ws = nullptr;
+    cudaError_t e = scratch_alloc(&ws, state_bytes + sync_bytes + tab_bytes, dc, stream);
+    if (e != cudaSuccess) return (int)e;
+    float* xstate = reinterpret_cast<float*>(ws);
+    int* xsync = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + state_bytes);
+    int* utab = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + state_bytes + sync_bytes);
+    gdr_units_mixed_kernel<<<1, 256, 0, stream>>>(p.B, p.T, mp.uncut_clips, mp.nseg, mp.seg_chunks, utab, xsync, (int)(sync_bytes / sizeof(int)));
+    count_launch();
+    gdr_chunk_kernel<true, false><<<entries * H, kThreads, kSmemBytes, stream>>>(mq, mk, mv, mo, pp, pp.T, 1, FastDiv::make(1u), 0, 0, xstate, xsync,
+                                                                                utab, nullptr);
+    count_launch();
+    const cudaError_t le = cudaGetLastError();
+    cudaFreeAsync(ws, stream);
+    return (int)le;
+}
+
+}  // namespace
+
+// Work units of an inference launch of this problem: out = {units, uncut clips, cut clips, segments of a cut clip}; returns 1 for
+// the mixed plan, 0 for the uniform one (out[1] = 0, out[2] = B, out[3] = segments per chain).
+int chunked_plan_units(const GdkvmGdrParams& p, int sms, int out[4]) {
+    sms = sms > 0 ? sms : 148;
+    MixedPlan mp;
+    if (mixed_plan_for(p, sms, &mp)) {
+        out[0] = (mp.uncut_clips + mp.cut_clips * mp.nseg) * p.H; out[1] = mp.uncut_clips; out[2] = mp.cut_clips; out[3] = mp.nseg;
+        return 1;
+    }
+    const int ns = chunked_segments(p, sms);
+    out[0] = p.B * p.H * ns; out[1] = 0; out[2] = p.B; out[3] = ns;
+    return 0;
 }
 
 int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream, void* chunk_states) {
@@ -1274,6 +1428,12 @@ int launch_chunked(const GdkvmGdrParams& p, cudaStream_t stream, void* chunk_sta
     if (chunk_states != nullptr) { pf.flags |= GDKVM_FLAG_FLAT_CHUNKS; pf.flags &= ~GDKVM_FLAG_FRAME_CHUNKS; }
     int nseg = (capturing && !dc->mempools) ? 1 : chunked_segments(pf, dc->sms);
     int seg_chunks = (nc + nseg - 1) / nseg;
+    // more than one wave of equal chains, flat tiling, the library's own choice of segments, a batch that is one packed token
+    // stream in memory: cut only the clips of the ragged last wave (pick_mixed) and run through the unit-table kernel
+    if (chunk_states == nullptr && !(capturing && !dc->mempools)) {
+        MixedPlan mp;
+        if (mixed_plan_for(p, dc->sms, &mp)) return launch_chunked_mixed(p, mp, dc, stream);
+    }
     float* xstate = nullptr;
     int* xsync = nullptr;
     void* ws = nullptr;

@@ -28,6 +28,7 @@ int chunked_segments(const GdkvmGdrParams& p, int sms);
 // Shared host helpers (gdr_chunked_sm100.cu): the schedule simulation behind the time segments, and a stream-ordered scratch
 // allocation from the library's private per-device pool (*sms receives the device's SM count).  Return cudaError_t as int.
 int plan_time_segments(int chains, int chunks, int sms);
+int chunked_plan_units(const GdkvmGdrParams& p, int sms, int out[4]);
 int library_scratch_alloc(void** ws, size_t bytes, cudaStream_t stream, int* sms, bool* mempools);
 
 // Backward pass (gdr_bwd_sm100.cu)

@@ -24,7 +24,7 @@ import torch
 
 from . import _cabi
 
-__all__ = ["gdr_lkva", "gdr_lkva_out", "train_unsupported_reason", "qkvgb_project", "qkvgb_project_reference", "gdr_lkva_varlen", "gdr_lkva_varlen_out", "check_inputs", "chunk_gated_delta_rule", "l2norm", "plan", "plan_reason",
+__all__ = ["gdr_lkva", "gdr_lkva_out", "train_unsupported_reason", "qkvgb_project", "qkvgb_project_reference", "gdr_lkva_varlen", "gdr_lkva_varlen_out", "check_inputs", "chunk_gated_delta_rule", "l2norm", "plan", "plan_reason", "plan_units",
            "plan_segments", "launch_count"]
 
 _DT = {torch.float32: _cabi.GDKVM_F32, torch.bfloat16: _cabi.GDKVM_BF16}
@@ -702,6 +702,18 @@ def plan_segments(q, k, v, g, beta, *, frame_tokens: int = 0, flags: int = 0, sm
     if rc < 0:
         raise RuntimeError(f"gdkvm_gdr_plan_segments: {_cabi.strerror(rc)}")
     return rc
+
+
+def plan_units(q, k, v, g, beta, *, frame_tokens: int = 0, flags: int = 0, sm_count: int = 0) -> dict:
+    """The work units an inference call would be scheduled as (``gdkvm_gdr_plan_units``): ``{"mixed": bool, "units": n, "uncut_clips":
+    a, "cut_clips": b, "segments": s}``; host arithmetic only."""
+    _check(q, k, v, g, beta, None)
+    p = _make_params(q, k, v, g, beta, v, None, None, 1.0, frame_tokens, flags)
+    out = (ctypes.c_int32 * 4)()
+    rc = _cabi.load().gdkvm_gdr_plan_units(ctypes.byref(p), int(sm_count), out)
+    if rc < 0:
+        raise RuntimeError(f"gdkvm_gdr_plan_units: {_cabi.strerror(rc)}")
+    return {"mixed": rc == 1, "units": out[0], "uncut_clips": out[1], "cut_clips": out[2], "segments": out[3]}
 
 
 def launch_count() -> int:

@@ -760,3 +760,31 @@ def test_recurrent_kernel_two_columns_per_thread(op):
         assert max_rel_err(o, o_ref) <= (1e-5 if dtype == torch.float32 else TOL[dtype]) and max_rel_err(sT, s_ref) <= 1e-5
         o1, s1 = _run(op, q[:3], k[:3], v[:3], g[:3], beta[:3], S0[:3], flags=RECURRENT)          # 24 chains: one column per thread
         assert torch.equal(o1, o[:3]) and torch.equal(s1, sT[:3])
+
+
+def test_mixed_plan_is_bit_identical_to_the_uniform_plans(op):
+    """A batch that fills more than one wave of SMs is scheduled with whole waves of uncut chains and only the clips of the last
+    wave cut (gdkvm_gdr_plan_units): same bits as every uniform plan, with and without an initial state, in a CUDA graph too; a
+    strided batch view or an explicit segment count keeps the uniform plan."""
+    B, T, H, V = 40, 20 * 64 + 9, 8, 128                  # 320 chains on 148 SMs: 18 clips uncut, 22 clips in two segments
+    q, k, v, g, beta, S0 = _dev(*make_inputs(B, T, H, 64, V, seed=77, dtype=torch.bfloat16))
+    plan = op.plan_units(q, k, v, g, beta)
+    assert plan["mixed"] and plan["uncut_clips"] + plan["cut_clips"] == B and plan["cut_clips"] > 0 and plan["segments"] > 1
+    assert not op.plan_units(q, k, v, g, beta, flags=SEG(2))["mixed"] and not op.plan_units(q[::2], k[::2], v[::2], g[::2], beta[::2])["mixed"]
+    for s0 in (S0, None):
+        o_m, s_m = op.gdr_lkva(q, k, v, g, beta, None, s0, True, 0, CHUNKED)
+        for n in (1, 2, 3):
+            o_u, s_u = op.gdr_lkva(q, k, v, g, beta, None, s0, True, 0, CHUNKED | SEG(n))
+            assert torch.equal(o_m, o_u) and torch.equal(s_m, s_u), n
+    o = torch.zeros_like(o_m); sT = torch.zeros_like(s_m)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        op.gdr_lkva_out(q, k, v, g, beta, o, sT, None, None, 0, CHUNKED)
+    for _ in range(2):
+        o.zero_(); sT.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(o, o_m) and torch.equal(sT, s_m)
+    o_ref, s_ref = gdr_recurrent_ref(*[t[-2:].cpu() for t in (q, k, v, g, beta)], None, None)       # two of the cut clips against the oracle
+    assert max_rel_err(o_m[-2:].float().cpu(), o_ref) <= TOL[torch.bfloat16] and max_rel_err(s_m[-2:].cpu(), s_ref) <= TOL[torch.bfloat16]
