@@ -1346,7 +1346,9 @@ bool pick_mixed_cached(int B, int H, int nc, int sms, int uniform_seg_chunks, Mi
 
 // Whether an (inference) launch of this problem takes the mixed plan, and which.
 bool mixed_plan_for(const GdkvmGdrParams& p, int sms, MixedPlan* mp) {
-    const bool flat = p.frame_tokens <= 0 || (p.flags & GDKVM_FLAG_FLAT_CHUNKS) || (p.frame_tokens % 64 != 0 && !(p.flags & GDKVM_FLAG_FRAME_CHUNKS));
+    // flat 64-token tiling -- or frames of whole 64-token chunks, whose chunks are the flat ones
+    const bool flat = p.frame_tokens <= 0 || (p.flags & GDKVM_FLAG_FLAT_CHUNKS) || (p.frame_tokens % 64 != 0 && !(p.flags & GDKVM_FLAG_FRAME_CHUNKS)) ||
+                      (p.frame_tokens % 64 == 0 && p.T % p.frame_tokens == 0);
     if (!flat || ((p.flags >> 8) & 0xfu) != 0 || p.B <= 1 || (int64_t)p.B * p.T >= ((int64_t)1 << 31)) return false;
     if (p.q_stride[0] != (int64_t)p.T * p.q_stride[1] || p.k_stride[0] != (int64_t)p.T * p.k_stride[1] ||
         p.v_stride[0] != (int64_t)p.T * p.v_stride[1] || p.o_stride[0] != (int64_t)p.T * p.o_stride[1] ||

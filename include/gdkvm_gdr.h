@@ -159,7 +159,7 @@ int gdkvm_gdr_plan_segments(const GdkvmGdrParams* params, int sm_count);
  * The work units of gdkvm_gdr_fwd for this problem: out = {units, uncut clips, cut clips, segments of a cut clip}.  A batch of
  * equal-length clips that fills more than one wave of SMs is not cut uniformly: whole waves of chains stay uncut (a unit
  * boundary costs ~3 chunk periods) and only the clips left over for the last wave are cut, into about one unit per SM
- * ("mixed plan": flat 64-token tiling, no GDKVM_FLAG_SEGMENTS, a batch that is contiguous in memory; results are bit-identical
+ * ("mixed plan": flat 64-token tiling or frames of whole 64-token chunks, no GDKVM_FLAG_SEGMENTS, a batch that is contiguous in memory; results are bit-identical
  * to any other plan).  Returns 1 for the mixed plan, 0 for the uniform one (out[1] = 0, out[3] = gdkvm_gdr_plan_segments), negative
  * = GdkvmStatus.  Pure host arithmetic.
  */

@@ -776,6 +776,12 @@ def test_mixed_plan_is_bit_identical_to_the_uniform_plans(op):
         for n in (1, 2, 3):
             o_u, s_u = op.gdr_lkva(q, k, v, g, beta, None, s0, True, 0, CHUNKED | SEG(n))
             assert torch.equal(o_m, o_u) and torch.equal(s_m, s_u), n
+    # frames of whole 64-token chunks (the CAMUS case): the same chunks, the same plan, the same bits
+    fq, fk, fv, fg, fb = (t[:, :1280].contiguous() for t in (q, k, v, g, beta))
+    assert op.plan_units(fq, fk, fv, fg, fb, frame_tokens=128)["mixed"]
+    o_f, s_f = op.gdr_lkva(fq, fk, fv, fg, fb, None, None, True, 128, CHUNKED)
+    o_g, s_g = op.gdr_lkva(fq, fk, fv, fg, fb, None, None, True, 128, CHUNKED | SEG(1))
+    assert torch.equal(o_f, o_g) and torch.equal(s_f, s_g)
     o = torch.zeros_like(o_m); sT = torch.zeros_like(s_m)
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()
